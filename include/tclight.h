@@ -1,0 +1,92 @@
+/* tclight.h — C ABI of libtclight.so, the sm_100a implementation of TC-Light's two hot paths.
+ *
+ * The reference (Linketic/TC-Light) has no FFI layer: its "operator API" for these paths is the
+ * set of Python callables listed in SURVEY.md §8(b).  Each entry point below replaces the
+ * PyTorch/diffusers op sequence behind one of those callables; the citation names the reference
+ * lines it stands in for (paths relative to the reference root).  The Python mirror in
+ * tclight_b200/ binds these with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative TCL_ERR_* code; tcl_last_error() gives
+ *     the message of the last failure on the calling thread;
+ *   - all pointers are DEVICE pointers unless a parameter name ends in _host;
+ *   - functions enqueue work on `stream` and never synchronise, allocate or take ownership;
+ *   - "16-bit" activations are fp16 or bf16, selected by a TCL_DTYPE_* argument;
+ *   - image activations are NHWC, token activations are [tokens, channels] row-major.
+ */
+#ifndef TCLIGHT_H_
+#define TCLIGHT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* tcl_stream_t; /* == cudaStream_t */
+
+#define TCL_DTYPE_FP16 0
+#define TCL_DTYPE_BF16 1
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* tcl_last_error(void);
+int tcl_version(void);
+/* number of kernel launches issued through this library since the last reset (bench.py's
+ * gpu_launches counter) */
+long long tcl_launch_count(void);
+void tcl_launch_count_reset(void);
+
+/* ---- implicit GEMM (tcgen05) ------------------------------------------------------------
+ * Replaces cuDNN/cuBLAS behind diffusers' ResnetBlock2D convs, Downsample2D/Upsample2D convs,
+ * Transformer2DModel proj_in/proj_out, Attention.to_q/k/v/out and GEGLU/FF linears
+ * (in-repo restatements utils/VidToMe/pnp_utils.py:40-97,
+ * 110-164).  out[pixel, n] = sum_k A[pixel, k] * W[n, k] with K described as up to four
+ * segments (NHWC tensor, taps): taps==9 is a 3x3 window with zero padding 1, taps==1 a 1x1.
+ */
+#define TCL_IGEMM_MAX_SRC 4
+#define TCL_EPI_NHWC 0   /* out[pixel*out_pitch + n] = (acc + bias[n] + residual) * out_scale   */
+#define TCL_EPI_GEGLU 1  /* weights interleaved per 256 rows (128 value | 128 gate);
+                            out[pixel, N/2] = value * gelu(gate)                                 */
+#define TCL_EPI_HEADS 2  /* N = nsec * sec_cols; section i written to sec_ptr[i] either as
+                            [b, head, tok_pitch, d_pad] (sec_vt[i]==0) or transposed
+                            [b, head, d_pad, tok_pitch] (sec_vt[i]==1)                           */
+
+typedef struct {
+  const void* ptr; /* NHWC 16-bit, already offset to the first channel of this segment */
+  int64_t n, h, w; /* INPUT image grid */
+  int64_t c;       /* channels in this segment (multiple of 64) */
+  int64_t pitch;   /* elements between consecutive pixels (>= c, multiple of 8) */
+  int32_t taps;    /* 1 or 9 */
+  int32_t stride;  /* 1 or 2: input coordinate = stride * output coordinate + tap - pad */
+} tcl_igemm_src;
+
+typedef struct {
+  int32_t dtype;
+  int32_t num_src;
+  tcl_igemm_src src[TCL_IGEMM_MAX_SRC];
+  int32_t n_img, out_h, out_w; /* OUTPUT pixel grid; a token matrix [M,K] is n_img=1,out_h=1,out_w=M */
+  int32_t N;                   /* output columns */
+  int64_t K;                   /* sum over segments of taps*c; weight is [N, K] row-major 16-bit */
+  const void* weight;
+  const float* bias; /* [N] fp32 or NULL */
+  int32_t mode;      /* TCL_EPI_* */
+  /* TCL_EPI_NHWC / TCL_EPI_GEGLU */
+  void* out;
+  int64_t out_pitch;
+  const void* residual; /* NHWC 16-bit or NULL (TCL_EPI_NHWC only) */
+  int64_t res_pitch;
+  float out_scale; /* 0 is treated as 1 */
+  /* TCL_EPI_HEADS */
+  void* sec_ptr[3];
+  int32_t sec_vt[3];
+  int32_t sec_cols, heads, d, d_pad;
+  int64_t tok_per_batch, tok_pitch;
+} tcl_igemm_desc;
+
+int tcl_igemm(const tcl_igemm_desc* desc, tcl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCLIGHT_H_ */

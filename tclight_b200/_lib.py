@@ -1,0 +1,114 @@
+"""ctypes binding of libtclight.so (the C ABI declared in include/tclight.h).
+
+The library is the product: there is no Python/PyTorch fallback.  Importing this module
+without a built ``libtclight.so`` raises, and every wrapper raises ``TclError`` when a call
+returns a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtclight.so")
+
+TCL_DTYPE_FP16 = 0
+TCL_DTYPE_BF16 = 1
+TCL_EPI_NHWC = 0
+TCL_EPI_GEGLU = 1
+TCL_EPI_HEADS = 2
+TCL_IGEMM_MAX_SRC = 4
+
+
+class TclError(RuntimeError):
+    pass
+
+
+class IgemmSrc(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p),
+        ("n", C.c_int64),
+        ("h", C.c_int64),
+        ("w", C.c_int64),
+        ("c", C.c_int64),
+        ("pitch", C.c_int64),
+        ("taps", C.c_int32),
+        ("stride", C.c_int32),
+    ]
+
+
+class IgemmDesc(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32),
+        ("num_src", C.c_int32),
+        ("src", IgemmSrc * TCL_IGEMM_MAX_SRC),
+        ("n_img", C.c_int32),
+        ("out_h", C.c_int32),
+        ("out_w", C.c_int32),
+        ("N", C.c_int32),
+        ("K", C.c_int64),
+        ("weight", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("mode", C.c_int32),
+        ("out", C.c_void_p),
+        ("out_pitch", C.c_int64),
+        ("residual", C.c_void_p),
+        ("res_pitch", C.c_int64),
+        ("out_scale", C.c_float),
+        ("sec_ptr", C.c_void_p * 3),
+        ("sec_vt", C.c_int32 * 3),
+        ("sec_cols", C.c_int32),
+        ("heads", C.c_int32),
+        ("d", C.c_int32),
+        ("d_pad", C.c_int32),
+        ("tok_per_batch", C.c_int64),
+        ("tok_pitch", C.c_int64),
+    ]
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C tclight_b200/csrc`). tclight_b200 has no CPU/PyTorch fallback."
+        )
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+lib.tcl_last_error.restype = C.c_char_p
+lib.tcl_version.restype = C.c_int
+lib.tcl_launch_count.restype = C.c_longlong
+lib.tcl_launch_count_reset.restype = None
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib.tcl_last_error().decode("utf-8", "replace")
+        raise TclError(f"{what} failed (status {rc}): {msg}")
+
+
+def stream_ptr() -> C.c_void_p:
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dtype_code(t) -> int:
+    import torch
+
+    if t == torch.float16:
+        return TCL_DTYPE_FP16
+    if t == torch.bfloat16:
+        return TCL_DTYPE_BF16
+    raise TclError(f"unsupported activation dtype {t}; tclight kernels take fp16 or bf16")
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise TclError("tclight_b200 ops need CUDA tensors (no CPU path exists)")
+
+
+lib.tcl_igemm.argtypes = [C.POINTER(IgemmDesc), C.c_void_p]
+lib.tcl_igemm.restype = C.c_int
