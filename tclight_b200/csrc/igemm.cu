@@ -45,6 +45,7 @@ struct IgParams {
   void* out;                  // NHWC
   long long out_pitch;        // elements per pixel in out
   float out_scale;
+  int vec_ok;                 // out/residual pitches allow 16-byte accesses
   // head-split modes
   void* sec_ptr[3];
   int sec_vt[3];
@@ -247,7 +248,7 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
                 for (int j = 0; j < 8; ++j)
                   if (col + j < p.N) f[j] += p.bias[col + j];
               }
-              if (col + 8 <= p.N) {
+              if (col + 8 <= p.N && p.vec_ok) {
                 if (res) {
                   const uint4 r4 = *reinterpret_cast<const uint4*>(res + col);
                   const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
@@ -470,7 +471,10 @@ extern "C" int tcl_igemm(const tcl_igemm_desc* d, cudaStream_t stream) {
     p.tok_per_batch = d->tok_per_batch; p.tok_pitch = d->tok_pitch;
   } else {
     TCL_CHECK_ARG(d->out != nullptr, "tcl_igemm: null out");
-    TCL_CHECK_ARG(d->out_pitch % 8 == 0, "tcl_igemm: out_pitch %% 8");
+    p.vec_ok = (d->out_pitch % 8 == 0) && (d->residual == nullptr || d->res_pitch % 8 == 0) &&
+               ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) &&
+               ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0);
+    if (d->mode == TCL_EPI_GEGLU) TCL_CHECK_ARG(p.vec_ok, "tcl_igemm: GEGLU output must be 16-byte aligned with pitch %% 8 == 0");
   }
 
 #define TCL_IG_DISPATCH(BN_, ST_)                                            \
