@@ -86,6 +86,30 @@ typedef struct {
 
 int tcl_igemm(const tcl_igemm_desc* desc, tcl_stream_t stream);
 
+/* ---- attention (tcgen05) ----------------------------------------------------------------
+ * Replaces diffusers Attention + AttnProcessor2_0 -> F.scaled_dot_product_attention
+ * (utils/model_utils.py:66; restated utils/VidToMe/pnp_utils.py:40-97; called from
+ * utils/VidToMe/vidtome/patch.py:157, 178).  Operands are the head-split outputs of tcl_igemm
+ * (TCL_EPI_HEADS): q [batch*heads, tq_pitch, d_pad], k [kv_batch*heads, tk_pitch, d_pad],
+ * vt [kv_batch*heads, d_pad, tk_pitch], zero padded beyond d.  kv_batch = batch/kv_batch_div
+ * (cross-attention: every frame of a CFG half shares one text embedding, generate.py:295).
+ * out is token-major [batch, tq, heads*d].  Softmax is exact (two passes), scale 1/sqrt(d).
+ */
+typedef struct {
+  int32_t dtype;
+  int32_t batch, heads;
+  int32_t tq, tk;
+  int32_t d, d_pad; /* d_pad in {64, 128, 192} */
+  int32_t kv_batch_div;
+  int64_t tq_pitch, tk_pitch;
+  const void* q;
+  const void* k;
+  const void* vt;
+  void* out;
+} tcl_attn_desc;
+
+int tcl_attention(const tcl_attn_desc* desc, tcl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

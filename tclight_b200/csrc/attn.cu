@@ -1,0 +1,386 @@
+// tcgen05 attention for the SD-1.5 transformer blocks (diffusers
+// Attention + AttnProcessor2_0 -> F.scaled_dot_product_attention, call site
+// utils/model_utils.py:66; restated in utils/VidToMe/pnp_utils.py:40-97).
+//   O[b, t, h*d + :] = softmax(Q K^T / sqrt(d)) V      (no mask, no dropout)
+// Operands come from tcl_igemm's head-split epilogue:
+//   Q  [B*H, tq_pitch, d_pad]   K [Bkv*H, tk_pitch, d_pad]   V^T [Bkv*H, d_pad, tk_pitch]
+// with the head dim zero-padded to d_pad in {64,128,192} (head_dim 40/80/160) so every tile is
+// a 128-byte-swizzled K-major UMMA operand.
+//
+// Two-pass exact softmax (no accumulator rescaling): pass 1 runs S = Q K^T for every KV tile
+// and keeps only the row max; pass 2 recomputes S, forms P = exp2((S - max) * scale) in
+// registers, stores P as 16-bit into swizzled smem and accumulates O += P V in TMEM.
+// Warp roles: NQ softmax warpgroups (one 128-row Q tile each, ping-pong against the single MMA
+// issuer), one TMA warp, one MMA warp.
+#include "common.cuh"
+#include "tmap.h"
+#include "tclight.h"
+
+namespace tcl {
+
+struct AttnParams {
+  int tq, tk;          // valid query / key rows per (batch, head)
+  int heads, d;        // true head dim
+  int kv_batch_div;    // kv batch = q batch / kv_batch_div (cross-attention text broadcast)
+  int n_kv_tiles;
+  float scale_log2;    // log2(e) / sqrt(d)
+  void* out;           // [B, tq, heads*d]
+  long long out_pitch; // heads*d
+};
+
+struct AttnTmaps {
+  CUtensorMap q, k, vt;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int NQ, int DPAD, int KST, int VST, bool BF16>
+__global__ void __launch_bounds__(NQ * 128 + 64, 1)
+attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnParams p) {
+  using E = Elem<BF16>;
+  constexpr int NC = DPAD / 64;                    // 64-wide chunks of the head dim
+  constexpr uint32_t QK_TILE = 128 * DPAD * 2;     // one Q or K tile (NC chunk tiles of 16 KB)
+  constexpr uint32_t V_CHUNK = DPAD * 128;         // one 64-kv chunk of V^T: DPAD rows x 128 B
+  constexpr uint32_t V_TILE = 2 * V_CHUNK;
+  constexpr uint32_t P_TILE = 128 * 128 * 2;       // 2 chunk tiles of 16 KB
+  constexpr uint32_t OFF_Q = 0;
+  constexpr uint32_t OFF_K = OFF_Q + NQ * QK_TILE;
+  constexpr uint32_t OFF_V = OFF_K + KST * QK_TILE;
+  constexpr uint32_t OFF_P = OFF_V + VST * V_TILE;
+  constexpr uint32_t OFF_BAR = OFF_P + NQ * P_TILE;
+  constexpr uint32_t TMEM_NEED = NQ * (128 + DPAD);
+  constexpr uint32_t TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
+  constexpr int SOFT_THREADS = NQ * 128;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars;                  // 1
+  uint64_t* k_full = q_full + 1;            // KST
+  uint64_t* k_empty = k_full + KST;         // KST
+  uint64_t* v_full = k_empty + KST;         // VST
+  uint64_t* v_empty = v_full + VST;         // VST
+  uint64_t* s_full = v_empty + VST;         // NQ
+  uint64_t* s_empty = s_full + NQ;          // NQ
+  uint64_t* p_full = s_empty + NQ;          // NQ
+  uint64_t* p_empty = p_full + NQ;          // NQ
+  uint64_t* o_full = p_empty + NQ;          // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;                       // q batch*heads index
+  const int b = bh / p.heads, head = bh - b * p.heads;
+  const int kv_bh = (b / p.kv_batch_div) * p.heads + head;
+  const int q_row0 = blockIdx.x * (NQ * 128);
+  const int n_kv = p.n_kv_tiles;
+
+  if (threadIdx.x == SOFT_THREADS) {
+    tma_prefetch_desc(&tm.q);
+    tma_prefetch_desc(&tm.k);
+    tma_prefetch_desc(&tm.vt);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KST; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < VST; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < NQ; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == SOFT_THREADS / 32 + 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == SOFT_THREADS / 32) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, NQ * QK_TILE);
+      for (int q = 0; q < NQ; ++q)
+        for (int c = 0; c < NC; ++c)
+          tma_load_3d(smem + OFF_Q + q * QK_TILE + c * 16384, &tm.q, q_full, c * 64, q_row0 + q * 128, bh);
+      int kn = 0, vn = 0;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int j = 0; j < n_kv; ++j) {
+          {
+            const int st = kn % KST;
+            mbar_wait(&k_empty[st], ((kn / KST) & 1) ^ 1);
+            mbar_arrive_expect_tx(&k_full[st], QK_TILE);
+            for (int c = 0; c < NC; ++c)
+              tma_load_3d(smem + OFF_K + st * QK_TILE + c * 16384, &tm.k, &k_full[st], c * 64, j * 128, kv_bh);
+            ++kn;
+          }
+          if (pass == 1) {
+            const int st = vn % VST;
+            mbar_wait(&v_empty[st], ((vn / VST) & 1) ^ 1);
+            mbar_arrive_expect_tx(&v_full[st], V_TILE);
+            for (int c = 0; c < 2; ++c)
+              tma_load_3d(smem + OFF_V + st * V_TILE + c * V_CHUNK, &tm.vt, &v_full[st], j * 128 + c * 64, 0, kv_bh);
+            ++vn;
+          }
+        }
+      }
+    }
+  } else if (warp == SOFT_THREADS / 32 + 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(BF16, 128, 128);
+      constexpr uint32_t idesc_o = umma_idesc_f16(BF16, 128, DPAD);
+      int kn = 0, vn = 0;
+      int sn[NQ], pn[NQ];
+      for (int q = 0; q < NQ; ++q) { sn[q] = 0; pn[q] = 0; }
+      const uint32_t q_base = smem_u32(smem + OFF_Q);
+      const uint32_t k_base = smem_u32(smem + OFF_K);
+      const uint32_t v_base = smem_u32(smem + OFF_V);
+      const uint32_t p_base = smem_u32(smem + OFF_P);
+
+      auto issue_qk_all = [&]() {
+        const int st = kn % KST;
+        mbar_wait(&k_full[st], (kn / KST) & 1);
+        tcgen05_fence_after();
+        for (int q = 0; q < NQ; ++q) {
+          mbar_wait(&s_empty[q], (sn[q] & 1) ^ 1);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const uint64_t a = umma_desc_k_sw128(q_base + q * QK_TILE + c * 16384);
+            const uint64_t bd = umma_desc_k_sw128(k_base + st * QK_TILE + c * 16384);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(tmem_base + q * 128, a + 2 * k, bd + 2 * k, idesc_s, (c | k) != 0);
+          }
+          umma_commit(&s_full[q]);
+          ++sn[q];
+        }
+        umma_commit(&k_empty[st]);
+        ++kn;
+      };
+
+      mbar_wait(q_full, 0);
+      tcgen05_fence_after();
+      // pass 1: scores only
+      for (int j = 0; j < n_kv; ++j) issue_qk_all();
+      // pass 2: scores (one tile ahead) + P V
+      issue_qk_all();
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) issue_qk_all();
+        const int st = vn % VST;
+        mbar_wait(&v_full[st], (vn / VST) & 1);
+        tcgen05_fence_after();
+        for (int q = 0; q < NQ; ++q) {
+          mbar_wait(&p_full[q], pn[q] & 1);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint64_t a = umma_desc_k_sw128(p_base + q * P_TILE + c * 16384);
+            const uint64_t bd = umma_desc_k_sw128(v_base + st * V_TILE + c * V_CHUNK);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(tmem_base + NQ * 128 + q * DPAD, a + 2 * k, bd + 2 * k, idesc_o, (j | c | k) != 0);
+          }
+          umma_commit(&p_empty[q]);
+          ++pn[q];
+        }
+        umma_commit(&v_empty[st]);
+        ++vn;
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ===================== softmax warpgroups =====================
+    const int q = warp >> 2;               // which Q tile
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t t_s = t_lane + q * 128;
+    const uint32_t t_o = t_lane + NQ * 128 + q * DPAD;
+    int it = 0;
+    float m = -INFINITY;
+    // ---- pass 1: row max ----
+    for (int j = 0; j < n_kv; ++j, ++it) {
+      mbar_wait(&s_full[q], it & 1);
+      tcgen05_fence_after();
+      const int valid_cols = p.tk - j * 128;
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_s + c0, v);
+        tmem_ld_wait();
+        if (valid_cols >= c0 + 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < valid_cols) m = fmaxf(m, __uint_as_float(v[i]));
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&s_empty[q]);
+    }
+    const float m_s = m * p.scale_log2;
+    float l = 0.f;
+    uint8_t* p_tile = smem + OFF_P + q * P_TILE;
+    // ---- pass 2: P = exp2(S*scale - m*scale), O += P V ----
+    for (int j = 0; j < n_kv; ++j, ++it) {
+      mbar_wait(&s_full[q], it & 1);
+      tcgen05_fence_after();
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      tmem_ld_32x32b_x32(t_s + 0, s0);
+      tmem_ld_32x32b_x32(t_s + 32, s1);
+      tmem_ld_32x32b_x32(t_s + 64, s2);
+      tmem_ld_32x32b_x32(t_s + 96, s3);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(&s_empty[q]);
+      const int valid_cols = p.tk - j * 128;
+      uint32_t pk[64];
+      auto do_chunk = [&](uint32_t (&s)[32], int c0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float e0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_s));
+          float e1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_s));
+          if (valid_cols < 128) {
+            if (c0 + i >= valid_cols) e0 = 0.f;
+            if (c0 + i + 1 >= valid_cols) e1 = 0.f;
+          }
+          l += e0 + e1;
+          pk[(c0 + i) >> 1] = E::pack(e0, e1);
+        }
+      };
+      do_chunk(s0, 0);
+      do_chunk(s1, 32);
+      do_chunk(s2, 64);
+      do_chunk(s3, 96);
+      // wait until the previous P V MMA has finished reading this P tile
+      mbar_wait(&p_empty[q], (j & 1) ^ 1);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint8_t* rowp = p_tile + c * 16384 + row * 128;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int pu = u ^ (row & 7);
+          *reinterpret_cast<uint4*>(rowp + pu * 16) =
+              make_uint4(pk[c * 32 + u * 4 + 0], pk[c * 32 + u * 4 + 1], pk[c * 32 + u * 4 + 2], pk[c * 32 + u * 4 + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&p_full[q]);
+    }
+    // ---- epilogue: O / l ----
+    mbar_wait(o_full, 0);
+    tcgen05_fence_after();
+    const int t = q_row0 + q * 128 + row;
+    const float inv_l = 1.0f / l;
+    typename E::T* out = reinterpret_cast<typename E::T*>(p.out) +
+                         (static_cast<long long>(b) * p.tq + t) * p.out_pitch + head * p.d;
+#pragma unroll 1
+    for (int c0 = 0; c0 < p.d; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(t_o + c0, v);
+      tmem_ld_wait();
+      if (t < p.tq) {
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          o[i] = E::pack(__uint_as_float(v[2 * i]) * inv_l, __uint_as_float(v[2 * i + 1]) * inv_l);
+        *reinterpret_cast<uint4*>(out + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+        if (c0 + 8 < p.d) *reinterpret_cast<uint4*>(out + c0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == SOFT_THREADS / 32 + 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int NQ, int DPAD, int KST, int VST, bool BF16>
+static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, int bh, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)NQ * 128 * DPAD * 2 + (size_t)KST * 128 * DPAD * 2 +
+                          (size_t)VST * 2 * DPAD * 128 + (size_t)NQ * 128 * 128 * 2 + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NQ, DPAD, KST, VST, BF16>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_last_error("attention: cudaFuncSetAttribute(%zu B) failed: %s", smem, cudaGetErrorString(e));
+      return TCL_ERR_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((q_tiles + NQ - 1) / NQ, bh);
+  attn_kernel<NQ, DPAD, KST, VST, BF16><<<grid, NQ * 128 + 64, smem, stream>>>(tm, p);
+  TCL_CHECK_LAUNCH("tcl_attention");
+  return TCL_OK;
+}
+
+}  // namespace tcl
+
+using namespace tcl;
+
+extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
+  TCL_CHECK_ARG(a != nullptr, "tcl_attention: null descriptor");
+  TCL_CHECK_ARG(a->q && a->k && a->vt && a->out, "tcl_attention: null pointer");
+  TCL_CHECK_ARG(a->dtype == TCL_DTYPE_FP16 || a->dtype == TCL_DTYPE_BF16, "tcl_attention: dtype");
+  TCL_CHECK_ARG(a->d_pad == 64 || a->d_pad == 128 || a->d_pad == 192, "tcl_attention: d_pad=%d (64/128/192)", a->d_pad);
+  TCL_CHECK_ARG(a->d > 0 && a->d <= a->d_pad && a->d % 8 == 0, "tcl_attention: d=%d", a->d);
+  TCL_CHECK_ARG(a->batch > 0 && a->heads > 0 && a->tq > 0 && a->tk > 0, "tcl_attention: empty problem");
+  TCL_CHECK_ARG(a->kv_batch_div >= 1 && a->batch % a->kv_batch_div == 0, "tcl_attention: kv_batch_div");
+  TCL_CHECK_ARG(a->tq_pitch >= a->tq && a->tk_pitch >= a->tk && a->tk_pitch % 8 == 0, "tcl_attention: pitches");
+  const bool bf16 = a->dtype == TCL_DTYPE_BF16;
+  const int bh = a->batch * a->heads;
+  const int kv_bh = (a->batch / a->kv_batch_div) * a->heads;
+  AttnTmaps tm;
+  {
+    const uint64_t dims[3] = {(uint64_t)a->d_pad, (uint64_t)a->tq, (uint64_t)bh};
+    const uint64_t str[2] = {(uint64_t)a->d_pad * 2, (uint64_t)a->tq_pitch * a->d_pad * 2};
+    const uint32_t box[3] = {64, 128, 1}, es[3] = {1, 1, 1};
+    int rc = make_tmap(&tm.q, a->q, bf16, 3, dims, str, box, es, 128);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)a->d_pad, (uint64_t)a->tk, (uint64_t)kv_bh};
+    const uint64_t str[2] = {(uint64_t)a->d_pad * 2, (uint64_t)a->tk_pitch * a->d_pad * 2};
+    const uint32_t box[3] = {64, 128, 1}, es[3] = {1, 1, 1};
+    int rc = make_tmap(&tm.k, a->k, bf16, 3, dims, str, box, es, 128);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)a->tk, (uint64_t)a->d_pad, (uint64_t)kv_bh};
+    const uint64_t str[2] = {(uint64_t)a->tk_pitch * 2, (uint64_t)a->d_pad * a->tk_pitch * 2};
+    const uint32_t box[3] = {64, (uint32_t)a->d_pad, 1}, es[3] = {1, 1, 1};
+    int rc = make_tmap(&tm.vt, a->vt, bf16, 3, dims, str, box, es, 128);
+    if (rc) return rc;
+  }
+  AttnParams p;
+  p.tq = a->tq; p.tk = a->tk; p.heads = a->heads; p.d = a->d;
+  p.kv_batch_div = a->kv_batch_div;
+  p.n_kv_tiles = (a->tk + 127) / 128;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)a->d);
+  p.out = a->out;
+  p.out_pitch = (long long)a->heads * a->d;
+  const int q_tiles = (a->tq + 127) / 128;
+  if (a->d_pad == 64) {
+    return bf16 ? launch_attn<2, 64, 3, 2, true>(tm, p, q_tiles, bh, stream)
+                : launch_attn<2, 64, 3, 2, false>(tm, p, q_tiles, bh, stream);
+  } else if (a->d_pad == 128) {
+    return bf16 ? launch_attn<1, 128, 2, 2, true>(tm, p, q_tiles, bh, stream)
+                : launch_attn<1, 128, 2, 2, false>(tm, p, q_tiles, bh, stream);
+  } else {
+    return bf16 ? launch_attn<1, 192, 2, 1, true>(tm, p, q_tiles, bh, stream)
+                : launch_attn<1, 192, 2, 1, false>(tm, p, q_tiles, bh, stream);
+  }
+}
