@@ -110,6 +110,39 @@ typedef struct {
 
 int tcl_attention(const tcl_attn_desc* desc, tcl_stream_t stream);
 
+/* ---- normalisation / staging (HBM-bound) --------------------------------------------------
+ * GroupNorm(+SiLU) of diffusers ResnetBlock2D / Transformer2DModel / conv_norm_out over NHWC,
+ * reading the channel concat [x1 | x2] of an up-block skip connection on the fly (x2 may be
+ * NULL with c2 == 0).  stats_ws: 2*groups*n_img floats of scratch.  (SURVEY.md §8a row A5;
+ * utils/VidToMe/pnp_utils.py:110-164.)
+ */
+int tcl_groupnorm(int dtype, const void* x1, int c1, const void* x2, int c2, int n_img,
+                  long long pix_per_img, int groups, const float* gamma, const float* beta, float eps,
+                  int silu, float* stats_ws, void* out, tcl_stream_t stream);
+
+/* LayerNorm over the last dim of [rows, C] (BasicTransformerBlock.norm1/2/3,
+ * utils/VidToMe/vidtome/patch.py:146, 170, 187). */
+int tcl_layernorm(int dtype, const void* x, long long rows, int C, const float* gamma, const float* beta,
+                  float eps, void* out, tcl_stream_t stream);
+
+/* F.interpolate(mode="nearest") to (oh, ow) over NHWC (diffusers Upsample2D). */
+int tcl_upsample_nearest(const void* x, int n, int h, int w, int c, int oh, int ow, void* out,
+                         tcl_stream_t stream);
+
+#define TCL_LATENT_FP32 0
+#define TCL_LATENT_FP16 1
+#define TCL_LATENT_BF16 2
+/* pred_noise input staging (generate.py:298 cat([x, x]); utils/model_utils.py:35-40 concat of the
+ * condition latent): x / cond are strided 4-channel latent views, strides xs/cs = HOST arrays
+ * {image, channel, row, col} in elements; out = NHWC [2F, H, W, 64] 16-bit (channels 8..63 zero). */
+int tcl_stage_latent(int dtype, int latent_dtype, const void* x, const long long* xs_host, const void* cond,
+                     const long long* cs_host, int F, int H, int W, void* out, tcl_stream_t stream);
+
+/* CFG combine (generate.py:349-350) of the UNet output eps NHWC [2F, H, W, pitch] into a strided
+ * 4-channel latent view (os_host as above). */
+int tcl_cfg_store(int dtype, int latent_dtype, const void* eps, int pitch, float guidance_scale, int F, int H,
+                  int W, void* out, const long long* os_host, tcl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,3 +112,26 @@ def require_cuda(*tensors) -> None:
 
 lib.tcl_igemm.argtypes = [C.POINTER(IgemmDesc), C.c_void_p]
 lib.tcl_igemm.restype = C.c_int
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32),
+        ("batch", C.c_int32),
+        ("heads", C.c_int32),
+        ("tq", C.c_int32),
+        ("tk", C.c_int32),
+        ("d", C.c_int32),
+        ("d_pad", C.c_int32),
+        ("kv_batch_div", C.c_int32),
+        ("tq_pitch", C.c_int64),
+        ("tk_pitch", C.c_int64),
+        ("q", C.c_void_p),
+        ("k", C.c_void_p),
+        ("vt", C.c_void_p),
+        ("out", C.c_void_p),
+    ]
+
+
+lib.tcl_attention.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
+lib.tcl_attention.restype = C.c_int

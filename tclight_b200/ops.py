@@ -122,3 +122,37 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias=None, residual=None, out=
     res4 = None if residual is None else residual.view(1, 1, M, -1)
     igemm([(src, 1, 1)], weight, (1, 1, M), bias=bias, residual=res4, mode=mode, out=out.view(1, 1, M, n_out))
     return out
+
+
+def head_pad(d: int) -> int:
+    """Head dim padded to a multiple of the 64-element swizzle chunk (40->64, 80->128, 160->192)."""
+    dp = (d + 63) // 64 * 64
+    if dp > 192:
+        raise TclError(f"head_dim {d} not supported (max 192)")
+    return dp
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, tq: int, tk: int, d: int,
+              kv_batch_div: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T / sqrt(d)) v on head-split operands (see tcl_attention in tclight.h).
+
+    q [B, H, tq_pitch, d_pad], k [Bkv, H, tk_pitch, d_pad], vt [Bkv, H, d_pad, tk_pitch]
+    -> out [B, tq, H*d]
+    """
+    require_cuda(q, k, vt)
+    B, H, tq_pitch, d_pad = q.shape
+    Bkv, _, tk_pitch, _ = k.shape
+    if vt.shape != (Bkv, H, d_pad, tk_pitch) or not (q.is_contiguous() and k.is_contiguous() and vt.is_contiguous()):
+        raise TclError("attention operands must be contiguous head-split tensors")
+    if Bkv * kv_batch_div != B:
+        raise TclError("attention: kv batch mismatch")
+    if out is None:
+        out = torch.empty((B, tq, H * d), device=q.device, dtype=q.dtype)
+    a = L.AttnDesc()
+    a.dtype = dtype_code(q.dtype)
+    a.batch, a.heads, a.tq, a.tk, a.d, a.d_pad = B, H, tq, tk, d, d_pad
+    a.kv_batch_div = kv_batch_div
+    a.tq_pitch, a.tk_pitch = tq_pitch, tk_pitch
+    a.q, a.k, a.vt, a.out = q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr()
+    check(lib.tcl_attention(C.byref(a), stream_ptr()), "tcl_attention")
+    return out

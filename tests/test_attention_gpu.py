@@ -1,0 +1,44 @@
+"""GPU parity of the tcgen05 attention kernel vs torch fp32 softmax attention on the same
+16-bit inputs.  Tolerance: P is rounded to 16 bit before P·V (as in flash attention), output
+rounded once => rel-L2 <= 3e-3 (fp16) / 1.5e-2 (bf16)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float16: 3e-3, torch.bfloat16: 1.5e-2}
+
+
+def _mk(B, H, T, d, d_pad, dtype, dev, scale=1.0):
+    Tp = (T + 7) // 8 * 8
+    x = (torch.randn(B, H, T, d, device=dev) * scale).to(dtype)
+    pad = torch.zeros(B, H, Tp, d_pad, device=dev, dtype=dtype)
+    pad[:, :, :T, :d] = x
+    return x, pad
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,H,Tq,Tk,d,div", [
+    (2, 8, 300, 300, 40, 1),     # self-attention, ragged tiles
+    (2, 8, 1024, 1024, 40, 1),
+    (1, 8, 257, 640, 80, 1),
+    (2, 8, 130, 130, 160, 1),
+    (4, 8, 200, 154, 40, 2),     # cross-attention: 2 frames per CFG half share text K/V
+    (4, 8, 200, 77, 80, 2),
+    (2, 4, 64, 77, 16, 1),       # tiny-UNet head dim
+])
+def test_attention(cuda, dtype, B, H, Tq, Tk, d, div):
+    from tclight_b200 import ops
+
+    torch.manual_seed(0)
+    d_pad = ops.head_pad(d)
+    q, qp = _mk(B, H, Tq, d, d_pad, dtype, cuda, 1.5)
+    k, kp = _mk(B // div, H, Tk, d, d_pad, dtype, cuda, 1.5)
+    v, vp = _mk(B // div, H, Tk, d, d_pad, dtype, cuda)
+    vt = vp.transpose(2, 3).contiguous()
+    out = ops.attention(qp, kp, vt, Tq, Tk, d, kv_batch_div=div)
+    kk = k.float().repeat_interleave(div, dim=0)
+    vv = v.float().repeat_interleave(div, dim=0)
+    s = torch.einsum("bhqd,bhkd->bhqk", q.float(), kk) / d ** 0.5
+    ref = torch.einsum("bhqk,bhkd->bhqd", s.softmax(-1), vv).permute(0, 2, 1, 3).reshape(B, Tq, H * d)
+    err = ((out.float() - ref).norm() / ref.norm()).item()
+    assert err < TOL[dtype], err
