@@ -143,6 +143,36 @@ int tcl_stage_latent(int dtype, int latent_dtype, const void* x, const long long
 int tcl_cfg_store(int dtype, int latent_dtype, const void* eps, int pitch, float guidance_scale, int F, int H,
                   int W, void* out, const long long* os_host, tcl_stream_t stream);
 
+/* ---- VidToMe token merging ------------------------------------------------------------------
+ * bipartite_soft_matching_randframe (utils/VidToMe/vidtome/merge.py:20-159) and
+ * bipartite_soft_matching_2s (:343-463) as called by compute_merge (patch.py:14-91).
+ *
+ * normalize_split: merge.py:84-85 — metric / metric.norm(dim=-1), then split into src (a) and
+ *   dst (b).  Tokens are [x0 | x1] along the token axis (x1 may be NULL: n1 == 0); dst is the
+ *   contiguous token range [d0, d1), src every other token in order.  a_out [batch, n_src, C],
+ *   b_out [batch, n_dst, C].
+ * match: merge.py:87-97 — scores = a b^T rounded to the 16-bit type, node_max/node_idx = max over
+ *   dst (lowest index among ties).  align_batch != 0 concatenates the dst axes of the batch
+ *   samples (node_idx in [0, batch*n_dst), outputs [n_src]); otherwise outputs are [batch, n_src].
+ *   The score matrix is never written to memory.
+ * plan: merge.py:98-108 + the index algebra of merge()/unmerge() (:119-155) turned into two gather
+ *   maps shared by all batch samples: merge_map[n_src - r + n_dst] (merged row -> token) and
+ *   unmerge_map[n_src + n_dst] (token -> merged row).  `edge` is argsort(node_max, descending).
+ * gather_rows: out[b, i, :] = [x0 | x1][b, map[i], :] (+ add[b, i, :]) — merge, unmerge and the
+ *   residual add of patch.py:168-169 in one pass.
+ */
+size_t tcl_vidtome_match_workspace_bytes(int batch, int n_src);
+int tcl_vidtome_normalize_split(int dtype, const void* x0, long long n0, const void* x1, long long n1, int batch,
+                                int C, long long d0, long long d1, void* a_out, void* b_out, tcl_stream_t stream);
+int tcl_vidtome_match(int dtype, const void* a, const void* b, int batch, int n_src, int n_dst, int C,
+                      int align_batch, float* node_max, long long* node_idx, void* workspace,
+                      size_t workspace_bytes, tcl_stream_t stream);
+int tcl_vidtome_plan(const long long* edge, const long long* node_idx, int n_src, int n_dst, int r, long long d0,
+                     int* merge_map, int* unmerge_map, tcl_stream_t stream);
+int tcl_gather_rows(int dtype, const void* x0, long long n0, const void* x1, long long n1, const int* map,
+                    int map_per_batch, long long n_out, int batch, int C, const void* add, void* out,
+                    tcl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -135,3 +135,35 @@ class AttnDesc(C.Structure):
 
 lib.tcl_attention.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
 lib.tcl_attention.restype = C.c_int
+
+TCL_LATENT_FP32 = 0
+TCL_LATENT_FP16 = 1
+TCL_LATENT_BF16 = 2
+
+lib.tcl_groupnorm.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.tcl_groupnorm.restype = C.c_int
+lib.tcl_layernorm.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_float,
+                              C.c_void_p, C.c_void_p]
+lib.tcl_layernorm.restype = C.c_int
+lib.tcl_upsample_nearest.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p]
+lib.tcl_upsample_nearest.restype = C.c_int
+lib.tcl_stage_latent.argtypes = [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_longlong), C.c_void_p,
+                                 C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+lib.tcl_stage_latent.restype = C.c_int
+lib.tcl_cfg_store.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                              C.c_void_p, C.POINTER(C.c_longlong), C.c_void_p]
+lib.tcl_cfg_store.restype = C.c_int
+
+
+def latent_code(t) -> int:
+    import torch
+
+    if t == torch.float32:
+        return TCL_LATENT_FP32
+    if t == torch.float16:
+        return TCL_LATENT_FP16
+    if t == torch.bfloat16:
+        return TCL_LATENT_BF16
+    raise TclError(f"unsupported latent dtype {t}")

@@ -156,3 +156,92 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, tq: int, tk: i
     a.q, a.k, a.vt, a.out = q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr()
     check(lib.tcl_attention(C.byref(a), stream_ptr()), "tcl_attention")
     return out
+
+
+_gn_ws = {}
+
+
+def _stats_ws(dev, n):
+    key = (dev, n >= 0)
+    ws = _gn_ws.get(dev)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 4096), device=dev, dtype=torch.float32)
+        _gn_ws[dev] = ws
+    return ws
+
+
+def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
+              x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) over NHWC [n,h,w,c1] (optionally channel-concatenated with x2 [n,h,w,c2])."""
+    require_cuda(x1, x2, gamma, beta)
+    n, h, w, c1 = x1.shape
+    c2 = 0 if x2 is None else x2.shape[3]
+    if not x1.is_contiguous() or (x2 is not None and not x2.is_contiguous()):
+        raise TclError("groupnorm inputs must be contiguous NHWC")
+    if gamma.dtype != torch.float32 or gamma.numel() != c1 + c2:
+        raise TclError("groupnorm affine must be fp32 [C]")
+    if out is None:
+        out = torch.empty((n, h, w, c1 + c2), device=x1.device, dtype=x1.dtype)
+    ws = _stats_ws(x1.device, 2 * groups * n)
+    check(lib.tcl_groupnorm(dtype_code(x1.dtype), x1.data_ptr(), c1, 0 if x2 is None else x2.data_ptr(), c2, n, h * w,
+                            groups, gamma.data_ptr(), beta.data_ptr(), eps, int(silu), ws.data_ptr(), out.data_ptr(),
+                            stream_ptr()), "tcl_groupnorm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    require_cuda(x, gamma, beta)
+    C_ = x.shape[-1]
+    if not x.is_contiguous():
+        raise TclError("layernorm input must be contiguous")
+    rows = x.numel() // C_
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.tcl_layernorm(dtype_code(x.dtype), x.data_ptr(), rows, C_, gamma.data_ptr(), beta.data_ptr(), eps,
+                            out.data_ptr(), stream_ptr()), "tcl_layernorm")
+    return out
+
+
+def upsample_nearest(x: torch.Tensor, oh: int, ow: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    require_cuda(x)
+    n, h, w, c = x.shape
+    if not x.is_contiguous():
+        raise TclError("upsample input must be contiguous NHWC")
+    if out is None:
+        out = torch.empty((n, oh, ow, c), device=x.device, dtype=x.dtype)
+    check(lib.tcl_upsample_nearest(x.data_ptr(), n, h, w, c, oh, ow, out.data_ptr(), stream_ptr()),
+          "tcl_upsample_nearest")
+    return out
+
+
+def _strides4(t: torch.Tensor):
+    """Element strides {image, channel, row, col} of a 4-D [F, 4, H, W] latent view."""
+    arr = (C.c_longlong * 4)(*[int(s) for s in t.stride()])
+    return arr
+
+
+def stage_latent(x: torch.Tensor, cond: Optional[torch.Tensor], act_dtype, out: Optional[torch.Tensor] = None):
+    """x, cond: [F, 4, H, W] (any strides) -> NHWC [2F, H, W, 64] act_dtype (CFG halves duplicated)."""
+    require_cuda(x, cond)
+    F_, c, H, W = x.shape
+    if c != 4 or (cond is not None and (cond.shape != x.shape or cond.dtype != x.dtype)):
+        raise TclError("stage_latent expects matching [F,4,H,W] latents")
+    if out is None:
+        out = torch.empty((2 * F_, H, W, 64), device=x.device, dtype=act_dtype)
+    check(lib.tcl_stage_latent(dtype_code(act_dtype), L.latent_code(x.dtype), x.data_ptr(), _strides4(x),
+                               0 if cond is None else cond.data_ptr(), None if cond is None else _strides4(cond),
+                               F_, H, W, out.data_ptr(), stream_ptr()), "tcl_stage_latent")
+    return out
+
+
+def cfg_store(eps: torch.Tensor, guidance_scale: float, out_view: torch.Tensor) -> None:
+    """eps NHWC [2F, H, W, pitch>=4] -> out_view[F,4,H,W] = uncond + g (cond - uncond)."""
+    require_cuda(eps, out_view)
+    F2, H, W, pitch = eps.shape
+    F_ = F2 // 2
+    if out_view.shape != (F_, 4, H, W) or not eps.is_contiguous():
+        raise TclError("cfg_store shape mismatch")
+    check(lib.tcl_cfg_store(dtype_code(eps.dtype), L.latent_code(out_view.dtype), eps.data_ptr(), pitch,
+                            float(guidance_scale), F_, H, W, out_view.data_ptr(), _strides4(out_view), stream_ptr()),
+          "tcl_cfg_store")
