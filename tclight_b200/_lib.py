@@ -167,3 +167,18 @@ def latent_code(t) -> int:
     if t == torch.bfloat16:
         return TCL_LATENT_BF16
     raise TclError(f"unsupported latent dtype {t}")
+
+lib.tcl_vidtome_match_workspace_bytes.argtypes = [C.c_int, C.c_int]
+lib.tcl_vidtome_match_workspace_bytes.restype = C.c_size_t
+lib.tcl_vidtome_normalize_split.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int,
+                                            C.c_int, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.tcl_vidtome_normalize_split.restype = C.c_int
+lib.tcl_vidtome_match.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+lib.tcl_vidtome_match.restype = C.c_int
+lib.tcl_vidtome_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]
+lib.tcl_vidtome_plan.restype = C.c_int
+lib.tcl_gather_rows.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int,
+                                C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.tcl_gather_rows.restype = C.c_int

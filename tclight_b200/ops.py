@@ -245,3 +245,70 @@ def cfg_store(eps: torch.Tensor, guidance_scale: float, out_view: torch.Tensor) 
     check(lib.tcl_cfg_store(dtype_code(eps.dtype), L.latent_code(out_view.dtype), eps.data_ptr(), pitch,
                             float(guidance_scale), F_, H, W, out_view.data_ptr(), _strides4(out_view), stream_ptr()),
           "tcl_cfg_store")
+
+
+# ---------------------------------------------------------------------------------------------
+# VidToMe primitives
+# ---------------------------------------------------------------------------------------------
+def normalize_split(x0: torch.Tensor, x1: Optional[torch.Tensor], d0: int, d1: int):
+    """tokens = [x0 | x1] ([B, n0, C], [B, n1, C]); dst = tokens[:, d0:d1]; returns normalised
+    (a [B, n_src, C], b [B, n_dst, C])  (merge.py:84-85)."""
+    require_cuda(x0, x1)
+    B, n0, C_ = x0.shape
+    n1 = 0 if x1 is None else x1.shape[1]
+    if not x0.is_contiguous() or (x1 is not None and not x1.is_contiguous()):
+        raise TclError("normalize_split inputs must be contiguous")
+    n_dst = d1 - d0
+    n_src = n0 + n1 - n_dst
+    a = torch.empty((B, n_src, C_), device=x0.device, dtype=x0.dtype)
+    b = torch.empty((B, n_dst, C_), device=x0.device, dtype=x0.dtype)
+    check(lib.tcl_vidtome_normalize_split(dtype_code(x0.dtype), x0.data_ptr(), n0, 0 if x1 is None else x1.data_ptr(),
+                                          n1, B, C_, d0, d1, a.data_ptr(), b.data_ptr(), stream_ptr()),
+          "tcl_vidtome_normalize_split")
+    return a, b
+
+
+def vidtome_match(a: torch.Tensor, b: torch.Tensor, align_batch: bool):
+    """node_max (fp32 holding 16-bit-rounded scores), node_idx (int64) — merge.py:87-97."""
+    require_cuda(a, b)
+    B, n_src, C_ = a.shape
+    n_dst = b.shape[1]
+    shape = (n_src,) if align_batch else (B, n_src)
+    node_max = torch.empty(shape, device=a.device, dtype=torch.float32)
+    node_idx = torch.empty(shape, device=a.device, dtype=torch.int64)
+    wsb = lib.tcl_vidtome_match_workspace_bytes(B, n_src)
+    ws = torch.empty(wsb, device=a.device, dtype=torch.uint8)
+    check(lib.tcl_vidtome_match(dtype_code(a.dtype), a.data_ptr(), b.data_ptr(), B, n_src, n_dst, C_, int(align_batch),
+                                node_max.data_ptr(), node_idx.data_ptr(), ws.data_ptr(), wsb, stream_ptr()),
+          "tcl_vidtome_match")
+    return node_max, node_idx
+
+
+def vidtome_plan(edge: torch.Tensor, node_idx: torch.Tensor, n_src: int, n_dst: int, r: int, d0: int):
+    """-> (merge_map int32 [n_src-r+n_dst], unmerge_map int32 [n_src+n_dst])."""
+    require_cuda(edge, node_idx)
+    mm = torch.empty(n_src - r + n_dst, device=edge.device, dtype=torch.int32)
+    um = torch.empty(n_src + n_dst, device=edge.device, dtype=torch.int32)
+    check(lib.tcl_vidtome_plan(edge.data_ptr(), node_idx.data_ptr(), n_src, n_dst, r, d0, mm.data_ptr(), um.data_ptr(),
+                               stream_ptr()), "tcl_vidtome_plan")
+    return mm, um
+
+
+def gather_rows(x0: torch.Tensor, x1: Optional[torch.Tensor], idx_map: torch.Tensor, add: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b, i] = [x0 | x1][b, map[i]] (+ add[b, i]);  map int32 [n_out] (shared) or [B, n_out]."""
+    require_cuda(x0, x1, idx_map, add)
+    B, n0, C_ = x0.shape
+    n1 = 0 if x1 is None else x1.shape[1]
+    per_batch = idx_map.dim() == 2
+    n_out = idx_map.shape[-1]
+    if idx_map.dtype != torch.int32 or not idx_map.is_contiguous():
+        raise TclError("gather map must be contiguous int32")
+    if not x0.is_contiguous() or (x1 is not None and not x1.is_contiguous()) or (add is not None and not add.is_contiguous()):
+        raise TclError("gather_rows inputs must be contiguous")
+    if out is None:
+        out = torch.empty((B, n_out, C_), device=x0.device, dtype=x0.dtype)
+    check(lib.tcl_gather_rows(dtype_code(x0.dtype), x0.data_ptr(), n0, 0 if x1 is None else x1.data_ptr(), n1,
+                              idx_map.data_ptr(), int(per_batch), n_out, B, C_, 0 if add is None else add.data_ptr(),
+                              out.data_ptr(), stream_ptr()), "tcl_gather_rows")
+    return out

@@ -1,0 +1,51 @@
+"""Pins the oracle restatements against the UNMODIFIED reference code (imported through
+oracle/refshim.py).  Runs only where /root/reference exists (the build container)."""
+import copy
+
+import pytest
+import torch
+
+from oracle import refshim
+
+pytestmark = pytest.mark.skipif(not refshim.reference_available(), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return refshim.import_reference()
+
+
+class _Mod:
+    pass
+
+
+@pytest.mark.parametrize("F,n,C,hw", [(4, 64, 32, (8, 8)), (3, 64, 32, (8, 8)), (2, 256, 16, (16, 16)), (1, 64, 32, (8, 8))])
+def test_compute_merge_matches_reference(ref, F, n, C, hw):
+    from oracle import vidtome_ref as V
+
+    torch.manual_seed(0)
+    args = dict(max_downsample=2, generator=None, seed=123, batch_size=2, align_batch=True, merge_global=True,
+                global_merge_ratio=0.5, local_merge_ratio=0.6, global_rand=0.5, target_stride=4)
+    mod = _Mod()
+    mod.generator = torch.Generator().manual_seed(7)
+    state = V.MergeState(torch.Generator().manual_seed(7))
+    info = dict(size=hw, args=copy.deepcopy(args))
+    for it in range(4):   # several chunks: first seeds the pool, later ones merge against it
+        x = torch.randn(2 * F, n, C)
+        m, u, merged_ref = ref.patch.compute_merge(mod, x, info)
+        merged, unmerge, trace = V.compute_merge(state, x, hw, args)
+        assert torch.equal(merged, merged_ref), f"merged tokens differ at chunk {it}"
+        y = torch.randn_like(merged)
+        assert torch.equal(unmerge(y), u(y)), f"unmerge differs at chunk {it}"
+        assert torch.equal(state.global_tokens, mod.global_tokens)
+
+
+def test_compute_merge_skips_low_res(ref):
+    from oracle import vidtome_ref as V
+
+    args = dict(max_downsample=2, generator=None, seed=123, batch_size=2, align_batch=True, merge_global=True,
+                global_merge_ratio=0.5, local_merge_ratio=0.6, global_rand=0.5, target_stride=4)
+    x = torch.randn(8, 4, 16)          # 16x16 image seen at downsample 8
+    state = V.MergeState(torch.Generator().manual_seed(1))
+    merged, unmerge, _ = V.compute_merge(state, x, (16, 16), args)
+    assert merged is x and state.global_tokens is None
