@@ -134,14 +134,21 @@ int tcl_upsample_nearest(const void* x, int n, int h, int w, int c, int oh, int 
 #define TCL_LATENT_BF16 2
 /* pred_noise input staging (generate.py:298 cat([x, x]); utils/model_utils.py:35-40 concat of the
  * condition latent): x / cond are strided 4-channel latent views, strides xs/cs = HOST arrays
- * {image, channel, row, col} in elements; out = NHWC [2F, H, W, 64] 16-bit (channels 8..63 zero). */
+ * {image, channel, row, col} in elements; out = NHWC [2F, H, W, 64] 16-bit (channels 8..63 zero);
+ * duplicate == 0 writes only the first F images. */
 int tcl_stage_latent(int dtype, int latent_dtype, const void* x, const long long* xs_host, const void* cond,
-                     const long long* cs_host, int F, int H, int W, void* out, tcl_stream_t stream);
+                     const long long* cs_host, int F, int H, int W, int duplicate, void* out, tcl_stream_t stream);
 
 /* CFG combine (generate.py:349-350) of the UNet output eps NHWC [2F, H, W, pitch] into a strided
  * 4-channel latent view (os_host as above). */
 int tcl_cfg_store(int dtype, int latent_dtype, const void* eps, int pitch, float guidance_scale, int F, int H,
                   int W, void* out, const long long* os_host, tcl_stream_t stream);
+
+/* y[N] = W[N,K] (16-bit) * f(x[K]) + bias, one vector: TimestepEmbedding linear_1/linear_2 and the
+ * per-resnet time_emb_proj(SiLU(temb)) (utils/VidToMe/pnp_utils.py:135-137).  x, bias, y
+ * are fp32; silu_in applies SiLU to x; round16 rounds like a 16-bit nn.Linear would. */
+int tcl_gemv(int dtype, const void* W, const float* x, const float* bias, int N, int K, int silu_in, int round16,
+             float* y, tcl_stream_t stream);
 
 /* ---- VidToMe token merging ------------------------------------------------------------------
  * bipartite_soft_matching_randframe (utils/VidToMe/vidtome/merge.py:20-159) and

@@ -150,7 +150,7 @@ lib.tcl_upsample_nearest.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_
                                      C.c_void_p]
 lib.tcl_upsample_nearest.restype = C.c_int
 lib.tcl_stage_latent.argtypes = [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_longlong), C.c_void_p,
-                                 C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+                                 C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 lib.tcl_stage_latent.restype = C.c_int
 lib.tcl_cfg_store.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                               C.c_void_p, C.POINTER(C.c_longlong), C.c_void_p]
@@ -182,3 +182,7 @@ lib.tcl_vidtome_plan.restype = C.c_int
 lib.tcl_gather_rows.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int,
                                 C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.tcl_gather_rows.restype = C.c_int
+
+lib.tcl_gemv.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                         C.c_void_p]
+lib.tcl_gemv.restype = C.c_int

@@ -201,7 +201,7 @@ __global__ void upsample_nearest_kernel(const uint4* __restrict__ x, int n, int 
 template <bool BF16, typename TIn>
 __global__ void stage_latent_kernel(const TIn* __restrict__ x, long long xs_img, long long xs_c, long long xs_y, long long xs_x,
                                     const TIn* __restrict__ cond, long long cs_img, long long cs_c, long long cs_y, long long cs_x,
-                                    int F, int H, int W, void* __restrict__ out) {
+                                    int F, int H, int W, int halves, void* __restrict__ out) {
   using E = Elem<BF16>;
   const long long total = (long long)F * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -217,7 +217,7 @@ __global__ void stage_latent_kernel(const TIn* __restrict__ x, long long xs_img,
     uint4 o;
     o.x = E::pack(v[0], v[1]); o.y = E::pack(v[2], v[3]); o.z = E::pack(v[4], v[5]); o.w = E::pack(v[6], v[7]);
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 0; half < halves; ++half) {
       uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<typename E::T*>(out) + ((long long)half * total + i) * 64);
       dst[0] = o;
 #pragma unroll
@@ -253,6 +253,37 @@ __global__ void cfg_store_kernel(const void* __restrict__ eps, int pitch, float 
       }
       out[f * os_img + c * os_c + yy * os_y + xx * os_x] = (TOut)r;
     }
+  }
+}
+
+// y = W x + b for a single vector (time embedding MLP and the per-resnet time_emb_proj,
+// SURVEY.md B.1).  One warp per output row; optional SiLU on the input and 16-bit rounding of
+// the output (the reference runs these nn.Linear layers in the UNet's 16-bit dtype).
+template <bool BF16>
+__global__ void gemv_kernel(const void* __restrict__ W, const float* __restrict__ x, const float* __restrict__ bias,
+                            int N, int K, int silu_in, int round16, float* __restrict__ y) {
+  using E = Elem<BF16>;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const int lane = threadIdx.x & 31;
+  const typename E::T* w = reinterpret_cast<const typename E::T*>(W) + (long long)row * K;
+  float acc = 0.f;
+  for (int k = lane * 8; k < K; k += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(w + k);
+    const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = E::unpack(ww[j]);
+      float x0 = x[k + 2 * j], x1 = x[k + 2 * j + 1];
+      if (silu_in) { x0 = silu_f(x0); x1 = silu_f(x1); if (round16) { x0 = E::to_f(E::from_f(x0)); x1 = E::to_f(E::from_f(x1)); } }
+      acc += f.x * x0 + f.y * x1;
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float r = acc + (bias ? bias[row] : 0.f);
+    if (round16) r = E::to_f(E::from_f(r));
+    y[row] = r;
   }
 }
 
@@ -326,7 +357,7 @@ extern "C" int tcl_upsample_nearest(const void* x, int n, int h, int w, int c, i
 }
 
 extern "C" int tcl_stage_latent(int dtype, int latent_dtype, const void* x, const long long* xs, const void* cond,
-                                const long long* cs, int F, int H, int W, void* out, cudaStream_t stream) {
+                                const long long* cs, int F, int H, int W, int duplicate, void* out, cudaStream_t stream) {
   TCL_CHECK_ARG(x && xs && out && F > 0 && H > 0 && W > 0, "tcl_stage_latent: args");
   TCL_CHECK_ARG(cond == nullptr || cs != nullptr, "tcl_stage_latent: cond strides");
   const long long total = (long long)F * H * W;
@@ -334,7 +365,7 @@ extern "C" int tcl_stage_latent(int dtype, int latent_dtype, const void* x, cons
   if (!cs) cs = z;
   const bool bf = dtype == TCL_DTYPE_BF16;
   const int g = grid_for(total, 256);
-#define TCL_STAGE(BF, T) stage_latent_kernel<BF, T><<<g, 256, 0, stream>>>((const T*)x, xs[0], xs[1], xs[2], xs[3], (const T*)cond, cs[0], cs[1], cs[2], cs[3], F, H, W, out)
+#define TCL_STAGE(BF, T) stage_latent_kernel<BF, T><<<g, 256, 0, stream>>>((const T*)x, xs[0], xs[1], xs[2], xs[3], (const T*)cond, cs[0], cs[1], cs[2], cs[3], F, H, W, duplicate ? 2 : 1, out)
   if (latent_dtype == TCL_LATENT_FP32) { if (bf) TCL_STAGE(true, float); else TCL_STAGE(false, float); }
   else if (latent_dtype == TCL_LATENT_FP16) { if (bf) TCL_STAGE(true, __half); else TCL_STAGE(false, __half); }
   else if (latent_dtype == TCL_LATENT_BF16) { if (bf) TCL_STAGE(true, __nv_bfloat16); else TCL_STAGE(false, __nv_bfloat16); }
@@ -357,5 +388,15 @@ extern "C" int tcl_cfg_store(int dtype, int latent_dtype, const void* eps, int p
   else { set_last_error("tcl_cfg_store: latent dtype %d", latent_dtype); return TCL_ERR_ARG; }
 #undef TCL_CFG
   TCL_CHECK_LAUNCH("tcl_cfg_store");
+  return TCL_OK;
+}
+
+extern "C" int tcl_gemv(int dtype, const void* W, const float* x, const float* bias, int N, int K, int silu_in,
+                        int round16, float* y, cudaStream_t stream) {
+  TCL_CHECK_ARG(W && x && y && N > 0 && K > 0 && K % 8 == 0, "tcl_gemv: args");
+  const int wpb = 8;
+  if (dtype == TCL_DTYPE_BF16) gemv_kernel<true><<<(N + wpb - 1) / wpb, wpb * 32, 0, stream>>>(W, x, bias, N, K, silu_in, round16, y);
+  else gemv_kernel<false><<<(N + wpb - 1) / wpb, wpb * 32, 0, stream>>>(W, x, bias, N, K, silu_in, round16, y);
+  TCL_CHECK_LAUNCH("tcl_gemv");
   return TCL_OK;
 }

@@ -221,17 +221,19 @@ def _strides4(t: torch.Tensor):
     return arr
 
 
-def stage_latent(x: torch.Tensor, cond: Optional[torch.Tensor], act_dtype, out: Optional[torch.Tensor] = None):
-    """x, cond: [F, 4, H, W] (any strides) -> NHWC [2F, H, W, 64] act_dtype (CFG halves duplicated)."""
+def stage_latent(x: torch.Tensor, cond: Optional[torch.Tensor], act_dtype, out: Optional[torch.Tensor] = None,
+                 duplicate: bool = True):
+    """x, cond: [F, 4, H, W] (any strides) -> NHWC [2F, H, W, 64] act_dtype (CFG halves duplicated),
+    or [F, H, W, 64] with duplicate=False."""
     require_cuda(x, cond)
     F_, c, H, W = x.shape
     if c != 4 or (cond is not None and (cond.shape != x.shape or cond.dtype != x.dtype)):
         raise TclError("stage_latent expects matching [F,4,H,W] latents")
     if out is None:
-        out = torch.empty((2 * F_, H, W, 64), device=x.device, dtype=act_dtype)
+        out = torch.empty(((2 if duplicate else 1) * F_, H, W, 64), device=x.device, dtype=act_dtype)
     check(lib.tcl_stage_latent(dtype_code(act_dtype), L.latent_code(x.dtype), x.data_ptr(), _strides4(x),
                                0 if cond is None else cond.data_ptr(), None if cond is None else _strides4(cond),
-                               F_, H, W, out.data_ptr(), stream_ptr()), "tcl_stage_latent")
+                               F_, H, W, int(duplicate), out.data_ptr(), stream_ptr()), "tcl_stage_latent")
     return out
 
 
@@ -311,4 +313,18 @@ def gather_rows(x0: torch.Tensor, x1: Optional[torch.Tensor], idx_map: torch.Ten
     check(lib.tcl_gather_rows(dtype_code(x0.dtype), x0.data_ptr(), n0, 0 if x1 is None else x1.data_ptr(), n1,
                               idx_map.data_ptr(), int(per_batch), n_out, B, C_, 0 if add is None else add.data_ptr(),
                               out.data_ptr(), stream_ptr()), "tcl_gather_rows")
+    return out
+
+
+def gemv(W: torch.Tensor, x: torch.Tensor, bias: Optional[torch.Tensor], silu_in: bool, round16: bool = True,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = W f(x) + b for one fp32 vector x [K]; W [N, K] 16-bit; returns fp32 [N]."""
+    require_cuda(W, x, bias)
+    N, K = W.shape
+    if x.dtype != torch.float32 or x.numel() != K or not W.is_contiguous():
+        raise TclError("gemv: x must be fp32 [K]")
+    if out is None:
+        out = torch.empty(N, device=W.device, dtype=torch.float32)
+    check(lib.tcl_gemv(dtype_code(W.dtype), W.data_ptr(), x.data_ptr(), 0 if bias is None else bias.data_ptr(), N, K,
+                       int(silu_in), int(round16), out.data_ptr(), stream_ptr()), "tcl_gemv")
     return out
