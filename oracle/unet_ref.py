@@ -311,3 +311,49 @@ def make_unet(seed: int = 0, dtype=torch.float32, **kw) -> UNet2DConditionModel:
     m = UNet2DConditionModel(**kw)
     torch.random.set_rng_state(g)
     return m.to(dtype).eval()
+
+
+# ---------------------------------------------------------------------------------------------
+# VidToMe-patched transformer block for the oracle UNet (reference patch.py:119-203 semantics,
+# built on oracle/vidtome_ref.py so it also runs where /root/reference does not exist).
+# ---------------------------------------------------------------------------------------------
+class ToMeBasicTransformerBlock(BasicTransformerBlock):
+    def forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None,
+                encoder_attention_mask=None, timestep=None, cross_attention_kwargs=None, class_labels=None):
+        from . import vidtome_ref as V
+
+        info = self._oracle_tome
+        if not hasattr(self, "_state"):
+            dev = hidden_states.device
+            gen = torch.Generator(device=dev)
+            gen.set_state(torch.cuda.get_rng_state() if dev.type == "cuda" else torch.get_rng_state())
+            self._state = V.MergeState(gen)
+        norm = self.norm1(hidden_states)
+        merged, unmerge, _ = V.compute_merge(self._state, norm, info["size"], info["args"])
+        attn = self.attn1(merged)
+        hidden_states = unmerge(attn) + hidden_states
+        hidden_states = self.attn2(self.norm2(hidden_states), encoder_hidden_states=encoder_hidden_states) + hidden_states
+        hidden_states = self.ff(self.norm3(hidden_states)) + hidden_states
+        return hidden_states
+
+
+def apply_oracle_patch(unet: UNet2DConditionModel, local_merge_ratio=0.6, merge_global=True, global_merge_ratio=0.5,
+                       max_downsample=2, batch_size=2, align_batch=True, target_stride=4, global_rand=0.5):
+    info = dict(size=None, args=dict(max_downsample=max_downsample, batch_size=batch_size, align_batch=align_batch,
+                                     merge_global=merge_global, global_merge_ratio=global_merge_ratio,
+                                     local_merge_ratio=local_merge_ratio, global_rand=global_rand,
+                                     target_stride=target_stride))
+    unet._oracle_tome = info
+    unet.register_forward_pre_hook(lambda mod, a: info.__setitem__("size", (a[0].shape[2], a[0].shape[3])))
+    for m in unet.modules():
+        if type(m) is BasicTransformerBlock:
+            m.__class__ = ToMeBasicTransformerBlock
+            m._oracle_tome = info
+    return unet
+
+
+def reset_oracle_pool(unet: UNet2DConditionModel):
+    """post_iter (reference generate_utils.py:235-238): drop every block's global-token pool."""
+    for m in unet.modules():
+        if hasattr(m, "_state"):
+            m._state.global_tokens = None
