@@ -150,6 +150,22 @@ int tcl_cfg_store(int dtype, int latent_dtype, const void* eps, int pitch, float
 int tcl_gemv(int dtype, const void* W, const float* x, const float* bias, int N, int K, int silu_in, int round16,
              float* y, tcl_stream_t stream);
 
+/* ---- sampler tail (HBM-bound, latent dtype = TCL_LATENT_*) ----------------------------------
+ * adain_blend: noises_t <- AdaIN(noises_t, noises); noises <- sqrt(alpha) noises_t + sqrt(1-alpha) noises
+ *   over `planes` = N*4 planes of `plane_elems` = h*w (generate.py:281-282; calc_mean_std /
+ *   adaptive_instance_normalization, utils/general_utils.py:137-156: unbiased var + 1e-5).
+ * scale_inplace: x *= s  (overlap rescale of later temporal windows, generate.py:276-278).
+ * dpm_step: diffusers DPMSolverMultistepScheduler.step (sde-dpmsolver++, midpoint) for one step:
+ *   x0 = (x - sigma_c_hat*eps)/alpha_c_hat;  x' = A x + B x0 [+ 0.5 B (x0 - x0_prev) inv_r0] + Cn z
+ *   with host-computed fp32 coefficients.  Writes x0 (history) and x'.
+ */
+int tcl_adain_blend(int latent_dtype, void* noises_t, void* noises, int planes, int plane_elems, float alpha,
+                    tcl_stream_t stream);
+int tcl_scale_inplace(int latent_dtype, void* x, long long n, float s, tcl_stream_t stream);
+int tcl_dpm_step(int latent_dtype, const void* eps, const void* x, const void* x0_prev, const float* z,
+                 void* x0_out, void* x_out, long long n, float sigma_c_hat, float alpha_c_hat, float A, float B,
+                 float Cn, float inv_r0, int second_order, tcl_stream_t stream);
+
 /* ---- VidToMe token merging ------------------------------------------------------------------
  * bipartite_soft_matching_randframe (utils/VidToMe/vidtome/merge.py:20-159) and
  * bipartite_soft_matching_2s (:343-463) as called by compute_merge (patch.py:14-91).

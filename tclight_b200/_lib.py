@@ -186,3 +186,12 @@ lib.tcl_gather_rows.restype = C.c_int
 lib.tcl_gemv.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                          C.c_void_p]
 lib.tcl_gemv.restype = C.c_int
+
+lib.tcl_adain_blend.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
+lib.tcl_adain_blend.restype = C.c_int
+lib.tcl_scale_inplace.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p]
+lib.tcl_scale_inplace.restype = C.c_int
+lib.tcl_dpm_step.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                             C.c_void_p]
+lib.tcl_dpm_step.restype = C.c_int

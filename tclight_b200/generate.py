@@ -1,0 +1,222 @@
+"""B200 mirror of the reference pipeline driver: ``Generator`` of generate.py:41-630 on top of
+``VidToMeGenerator`` (utils/VidToMe/generate_utils.py:20-238).  Same constructor, method names,
+argument meaning and RNG call pattern for the two hot paths:
+
+  * path 1: ``ddim_sample`` (:207-239), ``temporal_denoise`` (:241-284), ``pred_noise`` (:287-352),
+    ``get_chunks`` (generate_utils.py:174-205), ``pre_iter/post_iter`` (:228-238);
+  * path 2: ``exposure_align`` (:354-451), ``unique_tensor_optimization`` (:453-533)
+    (implemented in tclight_b200/postopt.py and bound here).
+
+Everything tensor-sized runs in libtclight.so.  Host-side differences that do not change
+results: chunks are passed to the UNet as strided *views* of the latent (no gather copies), the
+CFG combine writes straight into ``noises[chunk]``, and timesteps are host ints (no per-call
+device sync).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops, vidtome
+from ._lib import TclError
+
+
+def _as_range(idx: torch.Tensor):
+    """A chunk produced by get_chunks is a run of consecutive indices: return (lo, hi)."""
+    lo, hi = int(idx[0]), int(idx[-1]) + 1
+    if hi - lo != len(idx):
+        raise TclError("chunk indices must be consecutive")
+    return lo, hi
+
+
+class VidToMeGenerator(nn.Module):
+    """reference utils/VidToMe/generate_utils.py:20-96 (constructor wiring)."""
+
+    def __init__(self, pipe, scheduler, config):
+        super().__init__()
+        self.device = config.device
+        self.seed = config.seed
+        self.model_key = config.model_key
+        self.config = config
+        gene = config.generation
+        float_precision = gene.float_precision if "float_precision" in gene else config.float_precision
+        self.dtype = torch.float16 if float_precision == "fp16" else (torch.bfloat16 if float_precision == "bf16" else torch.float32)
+        self.pipe = pipe
+        self.unet = pipe.unet
+        self.vae = getattr(pipe, "vae", None)
+        self.tokenizer = getattr(pipe, "tokenizer", None)
+        self.text_encoder = getattr(pipe, "text_encoder", None)
+        self.n_timesteps = gene.n_timesteps
+        scheduler.set_timesteps(gene.n_timesteps, device=self.device)
+        self.scheduler = scheduler
+        self.batch_size = 2
+        self.control = gene.control
+        if self.control not in ("none", None) or config.sd_version == "depth":
+            raise NotImplementedError("PnP / ControlNet / depth conditioning are not involved in TC-Light "
+                                      "(configs/tclight_default.yaml:12,29) and are not implemented")
+        self.use_depth = self.use_controlnet = self.use_pnp = False
+        self.chunk_size = gene.chunk_size
+        self.chunk_ord = gene.chunk_ord
+        self.merge_global = gene.merge_global
+        self.local_merge_ratio = gene.local_merge_ratio
+        self.global_merge_ratio = gene.global_merge_ratio
+        self.global_rand = gene.global_rand
+        self.align_batch = gene.align_batch
+        self.prompt = gene.prompt
+        self.negative_prompt = gene.negative_prompt
+        self.guidance_scale = gene.guidance_scale
+        self.save_frame = gene.save_frame
+        self.work_dir = config.work_dir
+        if "mix" in self.chunk_ord:   # generate_utils.py:88-91
+            self.perm_div = float(self.chunk_ord.split("-")[-1]) if "-" in self.chunk_ord else 3.0
+            self.chunk_ord = "mix"
+        self.activate_vidtome()
+
+    def activate_vidtome(self):
+        # generate_utils.py:98-100 (max_downsample from the YAML is stored but never passed)
+        vidtome.apply_patch(self.pipe, self.local_merge_ratio, self.merge_global, self.global_merge_ratio,
+                            seed=self.seed, batch_size=self.batch_size,
+                            align_batch=self.use_pnp or self.align_batch, global_rand=self.global_rand)
+
+    def get_chunks(self, flen):
+        """generate_utils.py:174-205 — same CPU RNG calls in the same order."""
+        x_index = torch.arange(flen)
+        rand_first = np.random.randint(0, self.chunk_size) + 1
+        chunks = x_index[rand_first:].split(self.chunk_size, dim=0)
+        chunks = [x_index[:rand_first]] + list(chunks) if len(chunks[0]) > 0 else [x_index[:rand_first]]
+        if np.random.rand() > 0.5:
+            chunks = chunks[::-1]
+        if self.merge_global is False:
+            return chunks
+        if self.chunk_ord == "rand":
+            order = torch.randperm(len(chunks))
+        elif self.chunk_ord == "mix":
+            randord = torch.randperm(len(chunks)).tolist()
+            rand_len = int(len(randord) / self.perm_div)
+            seqord = sorted(randord[rand_len:])
+            if rand_len > 0:
+                randord = randord[:rand_len]
+                if abs(seqord[-1] - randord[-1]) < abs(seqord[0] - randord[-1]):
+                    seqord = seqord[::-1]
+                order = randord + seqord
+            else:
+                order = seqord
+        else:
+            order = torch.arange(len(chunks))
+        return [chunks[i] for i in order]
+
+    def pre_iter(self, x, t):
+        return None  # only PnP does work here (generate_utils.py:228-233)
+
+    def post_iter(self, x, t):
+        if self.merge_global:
+            vidtome.update_patch(self.pipe, global_tokens=None)   # generate_utils.py:235-238
+
+
+class Generator(VidToMeGenerator):
+    def __init__(self, pipe, scheduler, config):
+        super().__init__(pipe, scheduler, config)
+        self.config = config
+        self._init_generation(config.generation)
+        self._init_post_optimization(config.post_opt)
+        self.dataset = None
+        self.data_parser = getattr(pipe, "data_parser", None)
+        self.rng: Optional[List[torch.Generator]] = None
+
+    def _init_post_optimization(self, c):   # generate.py:50-64
+        self.apply_opt = c.apply_opt
+        self.lambda_dssim, self.lambda_flow, self.lambda_tv = c.lambda_dssim, c.lambda_flow, c.lambda_tv
+        self.epochs_exposure, self.epochs, self.opt_batch_size = c.epochs_exposure, c.epochs, c.batch_size
+        self.feature_lr = c.feature_lr
+        self.exposure_lr_init, self.exposure_lr_final = c.exposure_lr_init, c.exposure_lr_final
+        self.exposure_lr_delay_steps, self.exposure_lr_delay_mult = c.exposure_lr_delay_steps, c.exposure_lr_delay_mult
+
+    def _init_generation(self, g):          # generate.py:66-78
+        self.background_cond = g.background_cond
+        self.noise_mode = g.noise_mode
+        self.max_downsample = g.max_downsample
+        self.win_size_t = g.win_size_t
+        self.alpha_t = g.alpha_t
+        self.final_factor_t = g.final_factor_t
+        self.prompt_t = g.prompt_t
+        self.negative_prompt_t = g.negative_prompt_t
+
+    # ---------------------------------------------------------------- path 1
+    @torch.no_grad()
+    def ddim_sample(self, x, conds, conds_t, concat_conds=None):
+        """generate.py:207-239."""
+        timesteps = self.scheduler._timesteps_host
+        x = x.contiguous()
+        noises = torch.zeros_like(x)
+        noises_t = torch.zeros_like(x)
+        for i, t in enumerate(timesteps):
+            self.pre_iter(x, t)
+            for chunk in self.get_chunks(len(x)):
+                lo, hi = _as_range(chunk)
+                cc = concat_conds[lo:hi] if concat_conds is not None else None
+                self.pred_noise(x[lo:hi], conds, t, cc, batch_idx=chunk, out=noises[lo:hi])
+            if self.alpha_t > 0:
+                factor = self.final_factor_t ** min(i / len(timesteps), 1)
+                alpha_t = self.alpha_t * factor
+                noises_t, noises = self.temporal_denoise(x, conds_t, t, concat_conds, alpha_t, noises_t, noises)
+            x = self.scheduler.step(noises, t, x, generator=self.rng, return_dict=False)[0]
+            self.post_iter(x, t)
+        return x
+
+    @staticmethod
+    def temporal_windows(num_frames: int, win: int):
+        """Window plan of generate.py:246-260 -> (start indices, overlap list)."""
+        n_slices = math.ceil((num_frames - 1) / (win - 1))
+        if n_slices > 1:
+            total_overlap = n_slices * win - num_frames
+            overlap = total_overlap // (n_slices - 1)
+            last_overlap = overlap + total_overlap % (n_slices - 1)
+            overlap_list = [overlap] * (n_slices - 2) + [last_overlap]
+            cum = np.cumsum(overlap_list)
+            sl_idxs = [0] + [int((i + 1) * win - cum[i]) for i in range(n_slices - 1)]
+        else:
+            sl_idxs, overlap_list = [0], [0]
+        return sl_idxs, overlap_list
+
+    @torch.no_grad()
+    def temporal_denoise(self, x, conds_t, t, concat_conds, alpha_t, noises_t, noises):
+        """generate.py:241-284: yt-plane pass over overlapping frame windows."""
+        win = self.win_size_t
+        sl_idxs, overlap_list = self.temporal_windows(len(x), win)
+        chunks = self.get_chunks(x.shape[-1])
+        for idx, sl_i in enumerate(sl_idxs):
+            for chunk in chunks:
+                c0, c1 = _as_range(chunk)
+                # 'n c h w -> w c n h' as a view
+                xt = x[sl_i:sl_i + win, :, :, c0:c1].permute(3, 1, 0, 2)
+                cct = concat_conds[sl_i:sl_i + win, :, :, c0:c1].permute(3, 1, 0, 2) if concat_conds is not None else None
+                out = noises_t[sl_i:sl_i + win, :, :, c0:c1].permute(3, 1, 0, 2)
+                self.pred_noise(xt, conds_t, t, cct, batch_idx=chunk, sl_i=sl_i, out=out)
+            if sl_i > 0:
+                overlap_len = overlap_list[idx - 1]
+                ops.scale_inplace(noises_t[sl_i:sl_i + overlap_len], float(np.sqrt(0.5)))
+        ops.adain_blend(noises_t, noises, alpha_t)    # generate.py:281-282 (both updated in place)
+        return noises_t, noises
+
+    @torch.no_grad()
+    def pred_noise(self, x, cond, t, concat_conds=None, batch_idx=None, sl_i=None, out=None):
+        """generate.py:287-352.  ``cond`` = cat([uncond, cond]) [2, L, 768]; returns the CFG-combined
+        noise [F, 4, h, w] (written into ``out`` when given)."""
+        if out is None:
+            out = torch.empty(tuple(x.shape), device=x.device, dtype=x.dtype)
+        tt = int(t.item()) if torch.is_tensor(t) else int(t)
+        self.unet.predict_noise(x, concat_conds, cond, tt, self.guidance_scale, out)
+        return out
+
+    # ---------------------------------------------------------------- path 2 (postopt.py)
+    def exposure_align(self):
+        from .postopt import exposure_align
+        return exposure_align(self)
+
+    def unique_tensor_optimization(self):
+        from .postopt import unique_tensor_optimization
+        return unique_tensor_optimization(self)

@@ -328,3 +328,40 @@ def gemv(W: torch.Tensor, x: torch.Tensor, bias: Optional[torch.Tensor], silu_in
     check(lib.tcl_gemv(dtype_code(W.dtype), W.data_ptr(), x.data_ptr(), 0 if bias is None else bias.data_ptr(), N, K,
                        int(silu_in), int(round16), out.data_ptr(), stream_ptr()), "tcl_gemv")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# sampler tail
+# ---------------------------------------------------------------------------------------------
+def adain_blend(noises_t: torch.Tensor, noises: torch.Tensor, alpha: float) -> None:
+    """In place: noises_t <- AdaIN(noises_t, noises); noises <- sqrt(a) noises_t + sqrt(1-a) noises."""
+    require_cuda(noises_t, noises)
+    if noises_t.shape != noises.shape or noises_t.dtype != noises.dtype or noises.dim() != 4:
+        raise TclError("adain_blend: shape/dtype mismatch")
+    if not (noises_t.is_contiguous() and noises.is_contiguous()):
+        raise TclError("adain_blend: latents must be contiguous")
+    N, Cc, h, w = noises.shape
+    check(lib.tcl_adain_blend(L.latent_code(noises.dtype), noises_t.data_ptr(), noises.data_ptr(), N * Cc, h * w,
+                              float(alpha), stream_ptr()), "tcl_adain_blend")
+
+
+def scale_inplace(x: torch.Tensor, s: float) -> None:
+    require_cuda(x)
+    if not x.is_contiguous():
+        raise TclError("scale_inplace: tensor must be contiguous")
+    check(lib.tcl_scale_inplace(L.latent_code(x.dtype), x.data_ptr(), x.numel(), float(s), stream_ptr()),
+          "tcl_scale_inplace")
+
+
+def dpm_step(eps, x, x0_prev, z, coef: dict):
+    """One DPM-Solver++ SDE step; returns (x0, x_next) in the latent dtype."""
+    require_cuda(eps, x, x0_prev, z)
+    if z.dtype != torch.float32 or not (eps.is_contiguous() and x.is_contiguous() and z.is_contiguous()):
+        raise TclError("dpm_step: z must be contiguous fp32, latents contiguous")
+    x0 = torch.empty_like(eps)
+    xn = torch.empty_like(eps)
+    check(lib.tcl_dpm_step(L.latent_code(eps.dtype), eps.data_ptr(), x.data_ptr(), 0 if x0_prev is None else x0_prev.data_ptr(),
+                           z.data_ptr(), x0.data_ptr(), xn.data_ptr(), eps.numel(), coef["sigma_c_hat"], coef["alpha_c_hat"],
+                           coef["A"], coef["B"], coef["Cn"], coef["inv_r0"], int(coef["second_order"]), stream_ptr()),
+          "tcl_dpm_step")
+    return x0, xn

@@ -49,3 +49,36 @@ def test_compute_merge_skips_low_res(ref):
     state = V.MergeState(torch.Generator().manual_seed(1))
     merged, unmerge, _ = V.compute_merge(state, x, (16, 16), args)
     assert merged is x and state.global_tokens is None
+
+
+def test_ddim_sample_oracle_matches_reference_generator(ref):
+    """The restated sampler loop + oracle ToMe patch reproduce the reference's own
+    Generator.ddim_sample / temporal_denoise / pred_noise (run unmodified) bit for bit on CPU."""
+    import numpy as np
+    from oracle import harness, pipeline_ref as P
+    from oracle.unet_ref import make_unet
+
+    kw = dict(block_out_channels=(64, 128, 256, 256), cross_attention_dim=64)
+    gen_cfg = dict(n_timesteps=3, alpha_t=0.01, win_size_t=6)
+    N, h, w = 8, 16, 16
+    torch.manual_seed(3)
+    x = torch.randn(1, 4, h, w).repeat(N, 1, 1, 1)
+    cc = torch.randn(N, 4, h, w) * 0.18215
+    conds = torch.randn(2, 20, 64)
+    conds_t = torch.randn(2, 10, 64)
+
+    def seed_all():
+        torch.manual_seed(12345)
+        np.random.seed(12345)
+
+    u1 = make_unet(seed=0, **kw)
+    g, _ = harness.make_reference_generator(unet=u1, gen=gen_cfg)
+    seed_all()
+    g.rng = [torch.Generator().manual_seed(12345)] * N
+    want = g.ddim_sample(x.clone(), conds, conds_t, cc)
+
+    u2 = make_unet(seed=0, **kw)
+    seed_all()
+    got = P.ddim_sample_oracle(u2, x.clone(), conds, conds_t, cc, n_timesteps=3, alpha_t=0.01, win_size_t=6,
+                               rng=[torch.Generator().manual_seed(12345)] * N)
+    assert torch.equal(got, want)
