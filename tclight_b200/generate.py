@@ -145,26 +145,58 @@ class Generator(VidToMeGenerator):
         self.prompt_t = g.prompt_t
         self.negative_prompt_t = g.negative_prompt_t
 
+    # ---------------------------------------------------------------- multi-GPU sharding
+    def set_shard(self, rank: int, world: int):
+        """One process per GPU: the xy pass is sharded over contiguous frame ranges,
+        the yt pass over contiguous latent-column ranges; the per-rank partial noise tensors are
+        summed with one NCCL all-reduce each (zeros outside the own shard).  Each rank keeps its own
+        VidToMe pool, i.e. the multi-GPU semantics are "reference with the pool reset at shard
+        boundaries"; world == 1 is exactly the reference order."""
+        self._rank, self._world = int(rank), int(world)
+
+    def _my_range(self, n: int):
+        r, w = getattr(self, "_rank", 0), getattr(self, "_world", 1)
+        return (n * r) // w, (n * (r + 1)) // w
+
+    def _allreduce(self, t: torch.Tensor):
+        if getattr(self, "_world", 1) > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t)
+
     # ---------------------------------------------------------------- path 1
+    @torch.no_grad()
+    def denoise_step(self, x, conds, conds_t, concat_conds, i: int, noises, noises_t):
+        """Body of the sampling loop for step index i (generate.py:216-237)."""
+        timesteps = self.scheduler._timesteps_host
+        t = timesteps[i]
+        sharded = getattr(self, "_world", 1) > 1
+        self.pre_iter(x, t)
+        f0, f1 = self._my_range(len(x))
+        if sharded:
+            noises.zero_()
+        for chunk in self.get_chunks(f1 - f0):
+            lo, hi = _as_range(chunk)
+            lo, hi = lo + f0, hi + f0
+            cc = concat_conds[lo:hi] if concat_conds is not None else None
+            self.pred_noise(x[lo:hi], conds, t, cc, batch_idx=chunk, out=noises[lo:hi])
+        if sharded:
+            self._allreduce(noises)
+        if self.alpha_t > 0:
+            factor = self.final_factor_t ** min(i / len(timesteps), 1)
+            alpha_t = self.alpha_t * factor
+            noises_t, noises = self.temporal_denoise(x, conds_t, t, concat_conds, alpha_t, noises_t, noises)
+        x = self.scheduler.step(noises, t, x, generator=self.rng, return_dict=False)[0]
+        self.post_iter(x, t)
+        return x
+
     @torch.no_grad()
     def ddim_sample(self, x, conds, conds_t, concat_conds=None):
         """generate.py:207-239."""
-        timesteps = self.scheduler._timesteps_host
         x = x.contiguous()
         noises = torch.zeros_like(x)
         noises_t = torch.zeros_like(x)
-        for i, t in enumerate(timesteps):
-            self.pre_iter(x, t)
-            for chunk in self.get_chunks(len(x)):
-                lo, hi = _as_range(chunk)
-                cc = concat_conds[lo:hi] if concat_conds is not None else None
-                self.pred_noise(x[lo:hi], conds, t, cc, batch_idx=chunk, out=noises[lo:hi])
-            if self.alpha_t > 0:
-                factor = self.final_factor_t ** min(i / len(timesteps), 1)
-                alpha_t = self.alpha_t * factor
-                noises_t, noises = self.temporal_denoise(x, conds_t, t, concat_conds, alpha_t, noises_t, noises)
-            x = self.scheduler.step(noises, t, x, generator=self.rng, return_dict=False)[0]
-            self.post_iter(x, t)
+        for i in range(len(self.scheduler._timesteps_host)):
+            x = self.denoise_step(x, conds, conds_t, concat_conds, i, noises, noises_t)
         return x
 
     @staticmethod
@@ -187,10 +219,15 @@ class Generator(VidToMeGenerator):
         """generate.py:241-284: yt-plane pass over overlapping frame windows."""
         win = self.win_size_t
         sl_idxs, overlap_list = self.temporal_windows(len(x), win)
-        chunks = self.get_chunks(x.shape[-1])
+        w0, w1 = self._my_range(x.shape[-1])
+        sharded = getattr(self, "_world", 1) > 1
+        if sharded:
+            noises_t.zero_()
+        chunks = self.get_chunks(w1 - w0)
         for idx, sl_i in enumerate(sl_idxs):
             for chunk in chunks:
                 c0, c1 = _as_range(chunk)
+                c0, c1 = c0 + w0, c1 + w0
                 # 'n c h w -> w c n h' as a view
                 xt = x[sl_i:sl_i + win, :, :, c0:c1].permute(3, 1, 0, 2)
                 cct = concat_conds[sl_i:sl_i + win, :, :, c0:c1].permute(3, 1, 0, 2) if concat_conds is not None else None
@@ -199,6 +236,8 @@ class Generator(VidToMeGenerator):
             if sl_i > 0:
                 overlap_len = overlap_list[idx - 1]
                 ops.scale_inplace(noises_t[sl_i:sl_i + overlap_len], float(np.sqrt(0.5)))
+        if sharded:
+            self._allreduce(noises_t)
         ops.adain_blend(noises_t, noises, alpha_t)    # generate.py:281-282 (both updated in place)
         return noises_t, noises
 

@@ -14,6 +14,50 @@ from . import _lib as L
 from ._lib import TclError, check, dtype_code, lib, require_cuda, stream_ptr
 
 
+# ---------------------------------------------------------------------------------------------
+# optional per-kernel profiling (bench.py): CUDA events around each launch on the launching
+# stream + algorithmic FLOP counts.  Off by default (zero overhead).
+# ---------------------------------------------------------------------------------------------
+_PROFILE = None
+
+
+def profile_start():
+    global _PROFILE
+    _PROFILE = {}
+
+
+def profile_stop():
+    """-> {name: {flops, ms, launches}} (synchronises)."""
+    global _PROFILE
+    prof, _PROFILE = _PROFILE, None
+    out = {}
+    if not prof:
+        return out
+    torch.cuda.synchronize()
+    for name, recs in prof.items():
+        out[name] = {"flops": float(sum(r[2] for r in recs)), "ms": float(sum(r[0].elapsed_time(r[1]) for r in recs)),
+                     "launches": len(recs)}
+    return out
+
+
+class _Prof:
+    def __init__(self, name, flops):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *a):
+        if _PROFILE is not None:
+            self.e.record()
+            _PROFILE.setdefault(self.name, []).append((self.s, self.e, self.flops))
+        return False
+
+
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
@@ -108,7 +152,8 @@ def igemm(
             d.residual = residual.data_ptr()
             d.res_pitch = residual.stride(-2)
         ret = out
-    check(lib.tcl_igemm(C.byref(d), stream_ptr()), "tcl_igemm")
+    with _Prof("igemm_conv3x3" if any(tp == 9 for _, tp, _ in srcs) else "igemm_linear", 2.0 * n_img * oh * ow * N * ktot):
+        check(lib.tcl_igemm(C.byref(d), stream_ptr()), "tcl_igemm")
     return ret
 
 
@@ -154,7 +199,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, tq: int, tk: i
     a.kv_batch_div = kv_batch_div
     a.tq_pitch, a.tk_pitch = tq_pitch, tk_pitch
     a.q, a.k, a.vt, a.out = q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr()
-    check(lib.tcl_attention(C.byref(a), stream_ptr()), "tcl_attention")
+    with _Prof(f"attention_d{d_pad}", 4.0 * B * H * tq * tk * d):
+        check(lib.tcl_attention(C.byref(a), stream_ptr()), "tcl_attention")
     return out
 
 
@@ -280,9 +326,10 @@ def vidtome_match(a: torch.Tensor, b: torch.Tensor, align_batch: bool):
     node_idx = torch.empty(shape, device=a.device, dtype=torch.int64)
     wsb = lib.tcl_vidtome_match_workspace_bytes(B, n_src)
     ws = torch.empty(wsb, device=a.device, dtype=torch.uint8)
-    check(lib.tcl_vidtome_match(dtype_code(a.dtype), a.data_ptr(), b.data_ptr(), B, n_src, n_dst, C_, int(align_batch),
-                                node_max.data_ptr(), node_idx.data_ptr(), ws.data_ptr(), wsb, stream_ptr()),
-          "tcl_vidtome_match")
+    with _Prof("vidtome_match", 2.0 * B * n_src * n_dst * C_):
+        check(lib.tcl_vidtome_match(dtype_code(a.dtype), a.data_ptr(), b.data_ptr(), B, n_src, n_dst, C_, int(align_batch),
+                                    node_max.data_ptr(), node_idx.data_ptr(), ws.data_ptr(), wsb, stream_ptr()),
+              "tcl_vidtome_match")
     return node_max, node_idx
 
 
