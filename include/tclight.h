@@ -196,6 +196,49 @@ int tcl_gather_rows(int dtype, const void* x0, long long n0, const void* x1, lon
                     int map_per_batch, long long n_out, int batch, int C, const void* add, void* out,
                     tcl_stream_t stream);
 
+/* ---- two-stage temporal-consistency optimiser (HBM-bound, fp32) ------------------------------
+ * One call = one optimiser iteration of the reference loops, no host synchronisation:
+ *   tcl_exposure_iteration  Generator.exposure_align body, generate.py:392-436 (stage 1)
+ *   tcl_uvt_iteration       Generator.unique_tensor_optimization body, generate.py:494-517 (stage 2)
+ * covering OptDataset.__getitem__ (utils/dataloader.py:29-36), warp_flow (utils/flow_utils.py:5-16),
+ * l1_loss / relaxed_ms_ssim(start_level=1, data_range=1) / TVLoss (utils/loss_utils.py:25, 73-211,
+ * 324-339), SH2RGB (utils/sh_utils.py:117-118), index_select + its index_add backward, and
+ * torch.optim.Adam.step + zero_grad.
+ *   idx_host : HOST array of the batch's frame indices (what the DataLoader's sampler drew)
+ *   ids      : unq_inv as int32 [N*H*W] (data_parser.unq_inv, video_dataparser.py:59)
+ *   loss_out : device float[3] = {loss, loss_flow, loss_photometric} of this iteration (or NULL)
+ *   step     : 1-based Adam step count
+ */
+#define TCL_POSTOPT_MAX_BATCH 32
+typedef struct {
+  int32_t N, H, W;
+  const float* edited;     /* [N,3,H,W] OptDataset.edited_images                            */
+  const float* past_flows; /* [N,2,H,W]                                                      */
+  const float* mask_bwd;   /* [N,1,H,W] soft masks                                           */
+  const float* ypyr;       /* target pyramid from tcl_postopt_build_pyramid:
+                              [N,3,tcl_postopt_pyramid_elems(H,W)]                           */
+  float lambda_dssim, lambda_flow, lambda_tv;
+  void* workspace;         /* >= tcl_postopt_workspace_bytes(H, W, batch)                    */
+  size_t workspace_bytes;
+} tcl_postopt_ctx;
+
+size_t tcl_postopt_workspace_bytes(int H, int W, int max_batch);
+long long tcl_postopt_pyramid_elems(int H, int W);
+int tcl_postopt_build_pyramid(const float* edited, int N, int H, int W, float* ypyr, tcl_stream_t stream);
+int tcl_uvt_iteration(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, const int* ids, long long U,
+                      float* fdc, float* grad, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                      int step, float* loss_out, tcl_stream_t stream);
+int tcl_exposure_iteration(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, float* exposure, float* grad,
+                           float* m, float* v, float lr, float beta1, float beta2, float eps, int step,
+                           float* loss_out, tcl_stream_t stream);
+/* generate.py:477-479: fdc = RGB2SH(scatter_mean(edited, unq_inv)); cnt_ws = U floats of scratch */
+int tcl_uvt_init(const float* edited, const int* ids, int N, int H, int W, long long U, float* fdc, float* cnt_ws,
+                 tcl_stream_t stream);
+/* generate.py:529-531: out[N,3,H,W] = clamp(SH2RGB(fdc)[unq_inv], 0, 1) */
+int tcl_uvt_render(const float* fdc, const int* ids, int N, int H, int W, float* out, tcl_stream_t stream);
+/* OptDataset.exposure_align (utils/dataloader.py:38-42): edited <- clamp(edited x E[:3,:3] + E[:,3]) in place */
+int tcl_exposure_bake(float* edited, const float* exposure, int N, int H, int W, tcl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
