@@ -195,3 +195,38 @@ lib.tcl_dpm_step.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_vo
                              C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                              C.c_void_p]
 lib.tcl_dpm_step.restype = C.c_int
+
+
+TCL_POSTOPT_MAX_BATCH = 32
+
+
+class PostoptCtx(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("edited", C.c_void_p), ("past_flows", C.c_void_p), ("mask_bwd", C.c_void_p), ("ypyr", C.c_void_p),
+        ("lambda_dssim", C.c_float), ("lambda_flow", C.c_float), ("lambda_tv", C.c_float),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+lib.tcl_postopt_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+lib.tcl_postopt_workspace_bytes.restype = C.c_size_t
+lib.tcl_postopt_pyramid_elems.argtypes = [C.c_int, C.c_int]
+lib.tcl_postopt_pyramid_elems.restype = C.c_longlong
+lib.tcl_postopt_build_pyramid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+lib.tcl_postopt_build_pyramid.restype = C.c_int
+lib.tcl_uvt_iteration.argtypes = [C.POINTER(PostoptCtx), C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_longlong,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                  C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+lib.tcl_uvt_iteration.restype = C.c_int
+lib.tcl_exposure_iteration.argtypes = [C.POINTER(PostoptCtx), C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                       C.c_void_p, C.c_void_p]
+lib.tcl_exposure_iteration.restype = C.c_int
+lib.tcl_uvt_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p,
+                             C.c_void_p]
+lib.tcl_uvt_init.restype = C.c_int
+lib.tcl_uvt_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+lib.tcl_uvt_render.restype = C.c_int
+lib.tcl_exposure_bake.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+lib.tcl_exposure_bake.restype = C.c_int

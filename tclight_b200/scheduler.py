@@ -54,7 +54,7 @@ class DPMSolverMultistepSchedulerB200:
         return ((1 - w) * low_idx + w * high_idx).reshape(sigma.shape)
 
     def set_timesteps(self, num_inference_steps, device=None):
-        sigmas = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sigmas = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
         log_sigmas = np.log(sigmas)
         sigmas = np.flip(sigmas).copy()
         smin, smax, rho = sigmas[-1].item(), sigmas[0].item(), 7.0

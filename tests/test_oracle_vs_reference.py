@@ -82,3 +82,51 @@ def test_ddim_sample_oracle_matches_reference_generator(ref):
     got = P.ddim_sample_oracle(u2, x.clone(), conds, conds_t, cc, n_timesteps=3, alpha_t=0.01, win_size_t=6,
                                rng=[torch.Generator().manual_seed(12345)] * N)
     assert torch.equal(got, want)
+
+
+def _ref_generator_with_dataset(ref, edited, flows, masks, unq_inv, opt):
+    from oracle import harness
+    from oracle.unet_ref import make_unet
+
+    tiny = make_unet(seed=0, block_out_channels=(64, 64, 64, 64), cross_attention_dim=64)
+    g, _ = harness.make_reference_generator(unet=tiny, opt=opt)
+    g.dataset = ref.dataloader.OptDataset(edited.clone(), flows.clone(), masks.clone(), device="cpu")
+    g.data_parser.unq_inv = unq_inv.clone()
+    return g
+
+
+def test_stage2_oracle_matches_reference(ref):
+    """oracle/postopt_ref.stage2_uvt == the reference's own unique_tensor_optimization on CPU."""
+    from oracle import postopt_ref as O
+
+    edited, flows, masks, inv = O.synthetic_clip(n=6, h=176, w=192, seed=1)
+    opt = dict(epochs=2, batch_size=4)
+    g = _ref_generator_with_dataset(ref, edited, flows, masks, inv, opt)
+    torch.manual_seed(5)
+    want_img, want_loss = g.unique_tensor_optimization()
+    torch.manual_seed(5)
+    batches = O.draw_batches(6, 4, 2)
+    got_img, _, got_loss = O.stage2_uvt(edited, flows, masks, inv, batches)
+    assert len(got_loss) == len(want_loss)
+    assert max(abs(a - b) for a, b in zip(got_loss, want_loss)) < 1e-6
+    assert (got_img - want_img).abs().max().item() < 1e-5
+
+
+def test_stage1_oracle_matches_reference(ref, monkeypatch):
+    """oracle stage1_exposure == the reference's exposure_align (its hard-coded device="cuda" at
+    generate.py:378 is redirected to the CPU for this check only)."""
+    from oracle import postopt_ref as O
+
+    real_eye = torch.eye
+    monkeypatch.setattr(ref.generate.torch, "eye", lambda *a, device=None, **k: real_eye(*a, **k))
+    edited, flows, masks, inv = O.synthetic_clip(n=6, h=176, w=192, seed=2)
+    opt = dict(epochs_exposure=2, batch_size=4)
+    g = _ref_generator_with_dataset(ref, edited, flows, masks, inv, opt)
+    torch.manual_seed(6)
+    want_img, want_loss = g.exposure_align()
+    torch.manual_seed(6)
+    batches = O.draw_batches(6, 4, 2)
+    got_img, _, got_loss = O.stage1_exposure(edited, flows, masks, batches)
+    assert len(got_loss) == len(want_loss)
+    assert max(abs(a - b) for a, b in zip(got_loss, want_loss)) < 1e-6
+    assert (got_img - want_img).abs().max().item() < 1e-5

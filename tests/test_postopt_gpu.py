@@ -1,0 +1,141 @@
+"""Path-2 GPU parity: the CUDA optimiser iterations (tcl_exposure_iteration / tcl_uvt_iteration)
+vs the oracle (oracle/postopt_ref.py — torch autograd, pinned to the reference's own
+exposure_align / unique_tensor_optimization), same seeds, same batches, same device.
+
+Tolerances: gradients rel-L2 <= 1e-3; per-iteration loss abs diff <= 1e-5 (atomics
+reorder fp32 sums in both implementations); final images max-abs <= 2/255."""
+import types
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _gen(ds, unq_inv, **opt):
+    g = types.SimpleNamespace()
+    g.dataset = ds
+    g.data_parser = types.SimpleNamespace(unq_inv=unq_inv)
+    d = dict(lambda_dssim=0.2, lambda_flow=0.8, lambda_tv=0.05, epochs_exposure=2, epochs=2, opt_batch_size=4,
+             feature_lr=0.05, exposure_lr_init=0.01, exposure_lr_final=0.001, exposure_lr_delay_steps=0,
+             exposure_lr_delay_mult=0.0)
+    d.update(opt)
+    for k, v in d.items():
+        setattr(g, k, v)
+    return g
+
+
+@pytest.mark.parametrize("h,w", [(176, 192), (177, 203)])
+def test_stage2_gradient_matches_autograd(cuda, h, w):
+    import ctypes as C
+    from oracle import postopt_ref as O
+    from tclight_b200 import postopt as P
+    from tclight_b200._lib import lib, check, stream_ptr
+
+    edited, flows, masks, inv = O.synthetic_clip(n=5, h=h, w=w, seed=3, device=cuda)
+    ds = P.OptDataset(edited, flows, masks, device=cuda)
+    n = 5
+    idx = [3, 0, 4, 1]
+    # oracle gradient
+    size = int(inv.max().item()) + 1
+    mean_rgb = O.scatter_mean(edited.permute(0, 2, 3, 1).reshape(-1, 3), inv, size)
+    fdc0 = ((mean_rgb - 0.5) / O.SH_C0 + 0.3 * torch.randn(size, 3, device=cuda)).contiguous()   # push some values outside [0,1]
+    fdc = fdc0.clone().requires_grad_(True)
+    idx_t = torch.tensor(idx, device=cuda)
+    both = torch.cat([idx_t, (idx_t - 1).clamp(min=0)])
+    rgb = torch.index_select(fdc * O.SH_C0 + 0.5, 0, inv.reshape(n, h, w)[both].reshape(-1)).clamp(0, 1)
+    out = rgb.reshape(len(both), h, w, 3).permute(0, 3, 1, 2)
+    img, pre = out[:4], out[4:]
+    flow = O._flow_term(img, pre, flows[idx_t], masks[idx_t], idx_t)
+    photo = (1 - O.ms_ssim_relaxed(img, edited[idx_t])) * 0.2
+    loss = 0.2 * photo + 0.8 * flow + O.tv_loss(img, 0.05)
+    loss.backward()
+    # CUDA iteration with lr = 0: m = (1-beta1) * grad
+    ctx = P._Context(ds, 0.2, 0.8, 0.05, 4)
+    ids = inv.to(torch.int32).contiguous()
+    p = fdc0.clone()
+    g, m, v = (torch.zeros_like(p) for _ in range(3))
+    lo = torch.zeros(3, device=cuda)
+    arr = (C.c_int * 4)(*idx)
+    check(lib.tcl_uvt_iteration(C.byref(ctx.c), arr, 4, ids.data_ptr(), size, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                0.0, 0.9, 0.999, 1e-15, 1, lo.data_ptr(), stream_ptr()), "uvt")
+    grad = m / 0.1
+    rel = ((grad - fdc.grad).norm() / fdc.grad.norm()).item()
+    print(f"stage-2 gradient rel-L2 {rel:.2e}; loss {lo[0].item():.7f} vs {loss.item():.7f}")
+    assert rel < 1e-3
+    assert abs(lo[0].item() - loss.item()) < 1e-5
+    assert abs(lo[1].item() - flow.item()) < 1e-5 and abs(lo[2].item() - photo.item()) < 1e-5
+    assert g.abs().max().item() == 0 and torch.equal(p, fdc0)
+
+
+def test_stage1_gradient_matches_autograd(cuda):
+    import ctypes as C
+    from oracle import postopt_ref as O
+    from tclight_b200 import postopt as P
+    from tclight_b200._lib import lib, check, stream_ptr
+
+    h, w, n = 176, 192, 5
+    edited, flows, masks, inv = O.synthetic_clip(n=n, h=h, w=w, seed=4, device=cuda)
+    ds = P.OptDataset(edited, flows, masks, device=cuda)
+    idx = [2, 0, 4, 3]
+    e0 = (torch.eye(3, 4, device=cuda)[None].repeat(n, 1, 1) + 0.05 * torch.randn(n, 3, 4, device=cuda)).contiguous()
+    expo = e0.clone().requires_grad_(True)
+    idx_t = torch.tensor(idx, device=cuda)
+    both = torch.cat([idx_t, (idx_t - 1).clamp(min=0)])
+    pix = edited[both].permute(0, 2, 3, 1).reshape(len(both), h * w, 3)
+    out = (torch.bmm(pix, expo[both, :3, :3]) + expo[both, None, :3, 3]).clamp(0, 1).reshape(len(both), h, w, 3).permute(0, 3, 1, 2)
+    img, pre = out[:4], out[4:]
+    tgt = edited[idx_t]
+    photo = (img - tgt).abs().mean() * 0.8 + (1 - O.ms_ssim_relaxed(img, tgt)) * 0.2
+    flow = O._flow_term(img, pre, flows[idx_t], masks[idx_t], idx_t)
+    loss = 0.2 * photo + 0.8 * flow
+    loss.backward()
+    ctx = P._Context(ds, 0.2, 0.8, 0.05, 4)
+    p = e0.clone()
+    g, m, v = (torch.zeros_like(p) for _ in range(3))
+    lo = torch.zeros(3, device=cuda)
+    arr = (C.c_int * 4)(*idx)
+    check(lib.tcl_exposure_iteration(C.byref(ctx.c), arr, 4, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), 0.0, 0.9, 0.999,
+                                     1e-8, 1, lo.data_ptr(), stream_ptr()), "expo")
+    grad = m / 0.1
+    rel = ((grad - expo.grad).norm() / expo.grad.norm()).item()
+    print(f"stage-1 gradient rel-L2 {rel:.2e}; loss {lo[0].item():.7f} vs {loss.item():.7f}")
+    assert rel < 1e-3
+    assert abs(lo[0].item() - loss.item()) < 1e-5
+
+
+def test_stage2_run_matches_oracle(cuda):
+    from oracle import postopt_ref as O
+    from tclight_b200 import postopt as P
+
+    edited, flows, masks, inv = O.synthetic_clip(n=6, h=176, w=192, seed=1, device=cuda)
+    ds = P.OptDataset(edited, flows, masks, device=cuda)
+    gen = _gen(ds, inv, epochs=3)
+    torch.manual_seed(5)
+    got_img, got_loss = P.unique_tensor_optimization(gen)
+    torch.manual_seed(5)
+    batches = O.draw_batches(6, 4, 3)
+    want_img, _, want_loss = O.stage2_uvt(edited, flows, masks, inv, batches)
+    dl = max(abs(a - b) for a, b in zip(got_loss, want_loss))
+    di = (got_img - want_img).abs().max().item()
+    print(f"stage-2: {len(got_loss)} iterations, max loss diff {dl:.2e}, max image diff {di:.2e}; loss {want_loss[0]:.5f}->{want_loss[-1]:.5f}")
+    assert len(got_loss) == len(want_loss) and dl < 1e-5 and di <= 2 / 255
+
+
+def test_stage1_run_matches_oracle(cuda):
+    from oracle import postopt_ref as O
+    from tclight_b200 import postopt as P
+
+    edited, flows, masks, inv = O.synthetic_clip(n=6, h=176, w=192, seed=2, device=cuda)
+    ds = P.OptDataset(edited.clone(), flows, masks, device=cuda)
+    gen = _gen(ds, inv, epochs_exposure=3)
+    torch.manual_seed(6)
+    got_img, got_loss = P.exposure_align(gen)
+    torch.manual_seed(6)
+    batches = O.draw_batches(6, 4, 3)
+    want_img, want_expo, want_loss = O.stage1_exposure(edited, flows, masks, batches)
+    dl = max(abs(a - b) for a, b in zip(got_loss, want_loss))
+    di = (got_img - want_img).abs().max().item()
+    print(f"stage-1: {len(got_loss)} iterations, max loss diff {dl:.2e}, max image diff {di:.2e}")
+    assert len(got_loss) == len(want_loss) and dl < 1e-5 and di <= 2 / 255
+    assert (gen._exposure - want_expo).abs().max().item() < 1e-3
