@@ -2,8 +2,11 @@
 vs the oracle (oracle/postopt_ref.py — torch autograd, pinned to the reference's own
 exposure_align / unique_tensor_optimization), same seeds, same batches, same device.
 
-Tolerances: gradients rel-L2 <= 1e-3; per-iteration loss abs diff <= 1e-5 (atomics
-reorder fp32 sums in both implementations); final images max-abs <= 2/255."""
+Tolerances: per-pixel gradients rel-L2 <= 1e-4 (one UVT row per pixel); with shared
+UVT rows the flow term's contributions from a pixel and its flow-predecessor nearly cancel
+(+s and -s*sum(w)), so the NET fp32 gradient carries ~1e-3 relative rounding noise in both
+implementations: rel-L2 <= 5e-3 there; per-iteration loss abs diff <= 1e-5 (atomics reorder fp32
+sums in both implementations); final images max-abs <= 2/255."""
 import types
 
 import pytest
@@ -25,14 +28,16 @@ def _gen(ds, unq_inv, **opt):
     return g
 
 
-@pytest.mark.parametrize("h,w", [(176, 192), (177, 203)])
-def test_stage2_gradient_matches_autograd(cuda, h, w):
+@pytest.mark.parametrize("h,w,unique_rows", [(176, 192, False), (177, 203, False), (176, 192, True), (179, 201, True)])
+def test_stage2_gradient_matches_autograd(cuda, h, w, unique_rows):
     import ctypes as C
     from oracle import postopt_ref as O
     from tclight_b200 import postopt as P
     from tclight_b200._lib import lib, check, stream_ptr
 
     edited, flows, masks, inv = O.synthetic_clip(n=5, h=h, w=w, seed=3, device=cuda)
+    if unique_rows:
+        inv = torch.arange(5 * h * w, device=cuda)
     ds = P.OptDataset(edited, flows, masks, device=cuda)
     n = 5
     idx = [3, 0, 4, 1]
@@ -61,8 +66,8 @@ def test_stage2_gradient_matches_autograd(cuda, h, w):
                                 0.0, 0.9, 0.999, 1e-15, 1, lo.data_ptr(), stream_ptr()), "uvt")
     grad = m / 0.1
     rel = ((grad - fdc.grad).norm() / fdc.grad.norm()).item()
-    print(f"stage-2 gradient rel-L2 {rel:.2e}; loss {lo[0].item():.7f} vs {loss.item():.7f}")
-    assert rel < 1e-3
+    print(f"stage-2 gradient rel-L2 {rel:.2e} (unique rows: {unique_rows}); loss {lo[0].item():.7f} vs {loss.item():.7f}")
+    assert rel < (1e-4 if unique_rows else 5e-3)
     assert abs(lo[0].item() - loss.item()) < 1e-5
     assert abs(lo[1].item() - flow.item()) < 1e-5 and abs(lo[2].item() - photo.item()) < 1e-5
     assert g.abs().max().item() == 0 and torch.equal(p, fdc0)
