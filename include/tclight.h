@@ -218,7 +218,9 @@ typedef struct {
   const float* ypyr;       /* target pyramid from tcl_postopt_build_pyramid:
                               [N,3,tcl_postopt_pyramid_elems(H,W)]                           */
   float lambda_dssim, lambda_flow, lambda_tv;
-  void* workspace;         /* >= tcl_postopt_workspace_bytes(H, W, batch)                    */
+  int32_t max_batch;       /* largest n_batch that will be used with this workspace          */
+  void* workspace;         /* >= tcl_postopt_workspace_bytes(H, W, max_batch), ZERO-FILLED once
+                              by the caller before the first iteration                        */
   size_t workspace_bytes;
 } tcl_postopt_ctx;
 
@@ -238,6 +240,11 @@ int tcl_uvt_init(const float* edited, const int* ids, int N, int H, int W, long 
 int tcl_uvt_render(const float* fdc, const int* ids, int N, int H, int W, float* out, tcl_stream_t stream);
 /* OptDataset.exposure_align (utils/dataloader.py:38-42): edited <- clamp(edited x E[:3,:3] + E[:,3]) in place */
 int tcl_exposure_bake(float* edited, const float* exposure, int N, int H, int W, tcl_stream_t stream);
+
+/* test hook: one relaxed-SSIM level (utils/loss_utils.py:73-123) forward sums and/or backward
+ * of sum_p coef[p]*sum(map_p) for X, Y = [planes, h, w]; planes % 3 == 0. */
+int tcl_debug_ssim_level(const float* X, const float* Y, int planes, int h, int w, const float* coef, int use_ssim,
+                         float* sums, float* dX, tcl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -78,8 +78,13 @@ def ms_ssim_relaxed(x, y, start_level=1, data_range=1.0):
         if lvl < 4:
             terms.append(torch.relu(cs))
             pad = [s % 2 for s in x.shape[2:]]
-            x = F.avg_pool2d(x, kernel_size=2, padding=pad)
-            y = F.avg_pool2d(y, kernel_size=2, padding=pad)
+            # .contiguous(): torch 2.11 CUDA avg_pool2d BACKWARD is wrong for channels_last-strided
+            # inputs with padding (differs from its own CPU and contiguous-CUDA results, see
+            # tools/debug_pool.py); the reference's images are NHWC-strided views, so on a GPU it
+            # would hit that library bug whenever a pyramid level has an odd size.  The oracle pins
+            # the documented (CPU) semantics.
+            x = F.avg_pool2d(x.contiguous(), kernel_size=2, padding=pad)
+            y = F.avg_pool2d(y.contiguous(), kernel_size=2, padding=pad)
     terms.append(torch.relu(ss))
     stack = torch.stack(terms, dim=0)
     return torch.prod(stack ** w.view(-1, 1, 1), dim=0).mean()

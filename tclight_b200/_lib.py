@@ -205,6 +205,7 @@ class PostoptCtx(C.Structure):
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("edited", C.c_void_p), ("past_flows", C.c_void_p), ("mask_bwd", C.c_void_p), ("ypyr", C.c_void_p),
         ("lambda_dssim", C.c_float), ("lambda_flow", C.c_float), ("lambda_tv", C.c_float),
+        ("max_batch", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
@@ -230,3 +231,6 @@ lib.tcl_uvt_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int
 lib.tcl_uvt_render.restype = C.c_int
 lib.tcl_exposure_bake.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
 lib.tcl_exposure_bake.restype = C.c_int
+lib.tcl_debug_ssim_level.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
+lib.tcl_debug_ssim_level.restype = C.c_int

@@ -748,7 +748,8 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
                          float lr, float beta1, float beta2, float eps, int step, float* loss_out, cudaStream_t stream) {
   TCL_CHECK_ARG(c && idx_host && nb > 0 && nb <= MAXB, "postopt: batch size %d (max %d)", nb, MAXB);
   TCL_CHECK_ARG(c->edited && c->past_flows && c->mask_bwd && c->ypyr && c->workspace, "postopt: null context pointer");
-  TCL_CHECK_ARG(c->workspace_bytes >= ws_bytes(c->H, c->W, nb), "postopt: workspace too small");
+  TCL_CHECK_ARG(c->max_batch >= nb && c->max_batch <= MAXB, "postopt: batch %d exceeds ctx.max_batch %d", nb, c->max_batch);
+  TCL_CHECK_ARG(c->workspace_bytes >= ws_bytes(c->H, c->W, c->max_batch), "postopt: workspace too small");
   TCL_CHECK_ARG(step >= 1, "postopt: Adam step must start at 1");
   int rc = ensure_gauss();
   if (rc) return rc;
@@ -756,7 +757,7 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
   const long long P = (long long)H * W;
   Pyr py; make_pyr(H, W, &py);
   TCL_CHECK_ARG(py.h[4] >= 11 && py.w[4] >= 11, "postopt: image too small for 5-level MS-SSIM");
-  Ws w; carve(c->workspace, H, W, nb, &w);
+  Ws w; carve(c->workspace, H, W, c->max_batch, &w);   // fixed layout: G_pre must stay zero between iterations
   Batch bt; bt.n = nb;
   int n_valid = 0;
   for (int i = 0; i < nb; ++i) {
@@ -882,5 +883,34 @@ extern "C" int tcl_exposure_bake(float* edited, const float* exposure, int N, in
   const long long P = (long long)H * W;
   exposure_bake_kernel<<<gridp((long long)N * P, 256, 148 * 16), 256, 0, stream>>>(edited, exposure, P, N);
   TCL_CHECK_LAUNCH("tcl_exposure_bake");
+  return TCL_OK;
+}
+
+// Kernel-level test hooks (used by tests/test_postopt_gpu.py): one SSIM level in isolation.
+//   X, Y : [planes, h, w] fp32 (Y is indexed as frame = plane/3, channel = plane%3)
+//   sums : [planes][2] (cs sum, ssim sum) accumulated;  dX = d( sum_planes coef[p] * sum_map )/dX
+extern "C" int tcl_debug_ssim_level(const float* X, const float* Y, int planes, int h, int w, const float* coef, int use_ssim,
+                                    float* sums, float* dX, cudaStream_t stream) {
+  TCL_CHECK_ARG(X && Y && planes > 0 && planes % 3 == 0 && planes / 3 <= MAXB && h >= 11 && w >= 11, "tcl_debug_ssim_level: args");
+  int rc = ensure_gauss();
+  if (rc) return rc;
+  Batch bt; bt.n = planes / 3;
+  for (int i = 0; i < MAXB; ++i) bt.idx[i] = i < bt.n ? i : 0;
+  const float C1 = 1e-4f, C2 = 9e-4f;
+  const long long hw = (long long)h * w;
+  if (sums) {
+    cudaMemsetAsync(sums, 0, sizeof(float) * planes * 2, stream);
+    dim3 grid((w - 10 + ST - 1) / ST, (h - 10 + ST - 1) / ST, planes);
+    ssim_fwd_kernel<<<grid, 256, 0, stream>>>(X, hw, Y, 3 * hw, hw, bt, h, w, C1, C2, sums);
+    TCL_CHECK_LAUNCH("tcl_debug_ssim_level(fwd)");
+  }
+  if (dX) {
+    TCL_CHECK_ARG(coef != nullptr, "tcl_debug_ssim_level: coef");
+    const size_t bwd_smem = sizeof(float) * (2 * BR * BR + 5 * BP * BR + 3 * BP * BP);
+    cudaFuncSetAttribute(ssim_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem);
+    dim3 grid((w + BT - 1) / BT, (h + BT - 1) / BT, planes);
+    ssim_bwd_kernel<<<grid, 256, bwd_smem, stream>>>(X, hw, Y, 3 * hw, hw, bt, h, w, C1, C2, coef, use_ssim, nullptr, 0, 0, 0, 0, 0, dX, hw);
+    TCL_CHECK_LAUNCH("tcl_debug_ssim_level(bwd)");
+  }
   return TCL_OK;
 }

@@ -97,6 +97,7 @@ class _Context:
         c.edited, c.past_flows, c.mask_bwd = e.data_ptr(), ds.past_flows.data_ptr(), ds.mask_bwd.data_ptr()
         c.ypyr = self.ypyr.data_ptr()
         c.lambda_dssim, c.lambda_flow, c.lambda_tv = lambda_dssim, lambda_flow, lambda_tv
+        c.max_batch = batch
         c.workspace, c.workspace_bytes = self.ws.data_ptr(), wsb
         self.c = c
 
