@@ -175,3 +175,124 @@ def unique_tensor_optimization(gen) -> Tuple[torch.Tensor, List[float]]:
     check(lib.tcl_uvt_render(fdc.data_ptr(), ids.data_ptr(), N, H, W, images.data_ptr(), stream_ptr()), "tcl_uvt_render")
     gen._features_dc = fdc
     return images, losses[:step, 0].tolist()
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic workload + measurement helpers (bench.py, __graft_entry__.smoke)
+# ---------------------------------------------------------------------------------------------
+def synthetic_workload(n_frames: int, H: int, W: int, device, track_len: int = 10, seed: int = 0):
+    """Seeded synthetic stage-2 inputs of the named shape, generated on the device with torch ops
+    (test data, not the product path): a smooth texture translating by (2, 1) px/frame, noisy
+    'edited' frames, backward flows (-2, -1) + 0.25 px wobble, soft masks, and flow-tracked ids whose
+    tracks are cut every `track_len` frames (U / (N*H*W) ~ 1/track_len, in the 6-13 % range the
+    reference's voxelization produces on real clips)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    dx, dy = 2, 1
+    Hb, Wb = H + n_frames * dy, W + n_frames * dx
+    coarse = torch.rand(1, 3, Hb // 16 + 2, Wb // 16 + 2, device=device, generator=g)
+    big = torch.nn.functional.interpolate(coarse, size=(Hb, Wb), mode="bilinear", align_corners=False)[0]
+    edited = torch.empty((n_frames, 3, H, W), device=device, dtype=torch.float32)
+    ids = torch.empty((n_frames, H, W), device=device, dtype=torch.int32)
+    yy = torch.arange(H, device=device, dtype=torch.int64)[:, None]
+    xx = torch.arange(W, device=device, dtype=torch.int64)[None, :]
+    for f in range(n_frames):
+        oy, ox = (n_frames - 1 - f) * dy, (n_frames - 1 - f) * dx
+        edited[f] = (big[:, oy:oy + H, ox:ox + W] * 0.8 + 0.1 + 0.02 * torch.randn(3, H, W, device=device, generator=g)).clamp_(0, 1)
+        ids[f] = ((f // track_len) * (Hb * Wb) + (yy + oy) * Wb + (xx + ox)).to(torch.int32)
+    # compact the id space (what torch.unique(return_inverse) does in the reference's voxelization)
+    flat = ids.reshape(-1).long()
+    present = torch.zeros(int(flat.max().item()) + 1, device=device, dtype=torch.bool)
+    present[flat] = True
+    remap = torch.cumsum(present.to(torch.int32), 0, dtype=torch.int32) - 1
+    unq_inv = remap[flat].to(torch.int64)
+    del present, remap, flat, ids
+    flows = torch.empty((n_frames, 2, H, W), device=device, dtype=torch.float32)
+    flows[:, 0] = -dx + 0.25 * torch.sin(torch.arange(W, device=device).float() / 17.0)[None, None, :]
+    flows[:, 1] = -dy + 0.25 * torch.cos(torch.arange(H, device=device).float() / 13.0)[None, :, None]
+    masks = 0.5 + 0.5 * torch.rand((n_frames, 1, H, W), device=device, generator=g)
+    masks[:, :, :, :dx + 1] = 0
+    masks[:, :, :dy + 1, :] = 0
+    return edited, flows, masks, unq_inv
+
+
+def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: int = 0, world: int = 1, batch: int = 16):
+    """Times `iters` stage-2 iterations (16 frames each) at the named shape; returns a dict for the
+    bench JSON line.  Algorithmic bytes per iteration: 80*Bo*P + 84*U."""
+    import json
+    import os
+    import types
+
+    edited, flows, masks, unq_inv = synthetic_workload(n_frames, H, W, device)
+    ds = OptDataset(edited, flows, masks, device=device)
+    del edited, flows, masks
+    N = n_frames
+    Bo = batch
+    ids = unq_inv.to(torch.int32).contiguous()
+    U = int(unq_inv.max().item()) + 1
+    del unq_inv
+    ctx = _Context(ds, 0.2, 0.8, 0.05, Bo)
+    fdc = torch.empty((U, 3), device=device, dtype=torch.float32)
+    cnt = torch.empty(U, device=device, dtype=torch.float32)
+    check(lib.tcl_uvt_init(ds.edited_images.data_ptr(), ids.data_ptr(), N, H, W, U, fdc.data_ptr(), cnt.data_ptr(), stream_ptr()), "tcl_uvt_init")
+    del cnt
+    grad, m, v = (torch.zeros_like(fdc) for _ in range(3))
+    losses = torch.zeros((iters + 8, 3), device=device)
+    gcpu = torch.Generator().manual_seed(0)
+    lr = 0.05 * Bo / N
+
+    def run(k, step0):
+        for i in range(k):
+            idxs = torch.randperm(N, generator=gcpu)[:Bo].tolist()
+            arr, nb = _idx_array(idxs)
+            check(lib.tcl_uvt_iteration(C.byref(ctx.c), arr, nb, ids.data_ptr(), U, fdc.data_ptr(), grad.data_ptr(), m.data_ptr(),
+                                        v.data_ptr(), lr, 0.9, 0.999, 1e-15, step0 + i + 1, losses[(step0 + i) % len(losses)].data_ptr(),
+                                        stream_ptr()), "tcl_uvt_iteration")
+
+    run(3, 0)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    run(iters, 3)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / iters
+    P_ = H * W
+    alg_bytes = 80.0 * Bo * P_ + 84.0 * U
+    try:
+        with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) as f:
+            peak = json.load(f)["hbm_gbs"]
+        kind = "measured"
+    except Exception:
+        peak, kind = 6650.0, "fallback"
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    return {"metric": "stage2_iters_per_sec", "value": 1e3 / ms, "unit": "it/s", "ms_per_iter": ms, "frames": N, "batch": Bo,
+            "U": U, "U_over_NP": U / (N * P_), "algorithmic_bytes_per_iter": alg_bytes,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": kind, "unit": "GB/s", "frac": ach / peak, "traffic": None},
+            "loss_first_last": [losses[3, 0].item(), losses[(3 + iters - 1) % len(losses), 0].item()], "n_gpus": 1,
+            "note": "dense-Adam semantics (every UVT row updated every iteration, as torch.optim.Adam does)"}
+
+
+def smoke_check(device):
+    """One stage-2 and one stage-1 iteration on a tiny clip, checked against the oracle."""
+    import types
+
+    from oracle import postopt_ref as O
+
+    edited, flows, masks, inv = O.synthetic_clip(n=5, h=176, w=192, seed=1, device=device)
+    ds = OptDataset(edited.clone(), flows, masks, device=device)
+    gen = types.SimpleNamespace(dataset=ds, data_parser=types.SimpleNamespace(unq_inv=inv), lambda_dssim=0.2, lambda_flow=0.8,
+                                lambda_tv=0.05, epochs_exposure=1, epochs=1, opt_batch_size=4, feature_lr=0.05, exposure_lr_init=0.01,
+                                exposure_lr_final=0.001, exposure_lr_delay_steps=0, exposure_lr_delay_mult=0.0)
+    torch.manual_seed(5)
+    _, got = unique_tensor_optimization(gen)
+    torch.manual_seed(5)
+    _, _, want = O.stage2_uvt(edited, flows, masks, inv, O.draw_batches(5, 4, 1))
+    d2 = max(abs(a - b) for a, b in zip(got, want))
+    torch.manual_seed(6)
+    _, got1 = exposure_align(gen)
+    torch.manual_seed(6)
+    _, _, want1 = O.stage1_exposure(edited, flows, masks, O.draw_batches(5, 4, 1))
+    d1 = max(abs(a - b) for a, b in zip(got1, want1))
+    print(f"[smoke] path 2: stage-2 loss diff vs oracle {d2:.2e}, stage-1 {d1:.2e}")
+    if not (d2 < 1e-5 and d1 < 1e-5):
+        raise RuntimeError("smoke: optimiser parity failed")
