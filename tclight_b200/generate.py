@@ -165,12 +165,9 @@ class Generator(VidToMeGenerator):
 
     # ---------------------------------------------------------------- path 1
     @torch.no_grad()
-    def denoise_step(self, x, conds, conds_t, concat_conds, i: int, noises, noises_t):
-        """Body of the sampling loop for step index i (generate.py:216-237)."""
-        timesteps = self.scheduler._timesteps_host
-        t = timesteps[i]
+    def xy_pass(self, x, conds, t, concat_conds, noises):
+        """Per-chunk noise prediction over this rank's frame range (generate.py:220-224)."""
         sharded = getattr(self, "_world", 1) > 1
-        self.pre_iter(x, t)
         f0, f1 = self._my_range(len(x))
         if sharded:
             noises.zero_()
@@ -181,6 +178,15 @@ class Generator(VidToMeGenerator):
             self.pred_noise(x[lo:hi], conds, t, cc, batch_idx=chunk, out=noises[lo:hi])
         if sharded:
             self._allreduce(noises)
+        return noises
+
+    @torch.no_grad()
+    def denoise_step(self, x, conds, conds_t, concat_conds, i: int, noises, noises_t):
+        """Body of the sampling loop for step index i (generate.py:216-237)."""
+        timesteps = self.scheduler._timesteps_host
+        t = timesteps[i]
+        self.pre_iter(x, t)
+        self.xy_pass(x, conds, t, concat_conds, noises)
         if self.alpha_t > 0:
             factor = self.final_factor_t ** min(i / len(timesteps), 1)
             alpha_t = self.alpha_t * factor
@@ -215,8 +221,10 @@ class Generator(VidToMeGenerator):
         return sl_idxs, overlap_list
 
     @torch.no_grad()
-    def temporal_denoise(self, x, conds_t, t, concat_conds, alpha_t, noises_t, noises):
-        """generate.py:241-284: yt-plane pass over overlapping frame windows."""
+    def yt_pass(self, x, conds_t, t, concat_conds, noises_t, scale=None):
+        """yt-plane predictions over overlapping frame windows for this rank's latent-column range
+        (generate.py:246-278)."""
+        scale = ops.scale_inplace if scale is None else scale
         win = self.win_size_t
         sl_idxs, overlap_list = self.temporal_windows(len(x), win)
         w0, w1 = self._my_range(x.shape[-1])
@@ -235,9 +243,15 @@ class Generator(VidToMeGenerator):
                 self.pred_noise(xt, conds_t, t, cct, batch_idx=chunk, sl_i=sl_i, out=out)
             if sl_i > 0:
                 overlap_len = overlap_list[idx - 1]
-                ops.scale_inplace(noises_t[sl_i:sl_i + overlap_len], float(np.sqrt(0.5)))
+                scale(noises_t[sl_i:sl_i + overlap_len], float(np.sqrt(0.5)))
         if sharded:
             self._allreduce(noises_t)
+        return noises_t
+
+    @torch.no_grad()
+    def temporal_denoise(self, x, conds_t, t, concat_conds, alpha_t, noises_t, noises):
+        """generate.py:241-284: yt-plane pass, then AdaIN to the xy statistics and blend."""
+        self.yt_pass(x, conds_t, t, concat_conds, noises_t)
         ops.adain_blend(noises_t, noises, alpha_t)    # generate.py:281-282 (both updated in place)
         return noises_t, noises
 

@@ -1,0 +1,138 @@
+"""Host-side mirrors (no GPU): chunk planning, window plan, LR schedule, config loader, scheduler
+coefficients, optimiser batch order — against the oracle restatements (pinned to the reference)."""
+import math
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+
+def _gen_stub(**kw):
+    from tclight_b200.generate import VidToMeGenerator
+
+    g = types.SimpleNamespace(chunk_size=4, merge_global=True, chunk_ord="mix", perm_div=4.0)
+    g.__dict__.update(kw)
+    g.get_chunks = types.MethodType(VidToMeGenerator.get_chunks, g)
+    return g
+
+
+@pytest.mark.parametrize("n", [1, 3, 8, 30, 160, 300])
+@pytest.mark.parametrize("ord_", ["mix", "rand", "seq"])
+def test_get_chunks_matches_oracle_and_partitions(n, ord_):
+    from oracle.pipeline_ref import plan_chunks
+
+    g = _gen_stub(chunk_ord=ord_)
+    for seed in range(5):
+        np.random.seed(seed); torch.manual_seed(seed)
+        a = g.get_chunks(n)
+        np.random.seed(seed); torch.manual_seed(seed)
+        b = plan_chunks(n, 4, True, ord_, 4.0)
+        assert len(a) == len(b) and all(torch.equal(x, y) for x, y in zip(a, b))
+        allidx = torch.cat(a).sort().values
+        assert torch.equal(allidx, torch.arange(n))                      # a partition of the frames
+        assert all(1 <= len(c) <= 4 for c in a)
+        assert all(int(c[-1]) - int(c[0]) + 1 == len(c) for c in a)      # consecutive runs
+
+
+def test_temporal_window_plan():
+    from oracle.pipeline_ref import window_plan
+    from tclight_b200.generate import Generator
+
+    assert Generator.temporal_windows(300, 64) == ([0, 59, 118, 177, 236], [5, 5, 5, 5])
+    assert Generator.temporal_windows(30, 64) == ([0], [0])
+    for n in (2, 63, 64, 65, 127, 128, 171, 250, 600):
+        assert Generator.temporal_windows(n, 64) == window_plan(n, 64)
+        starts, _ = Generator.temporal_windows(n, 64)
+        assert starts[-1] + 64 >= n and all(b - a <= 64 for a, b in zip(starts, starts[1:]))
+
+
+def test_expon_lr_indexing():
+    from oracle.postopt_ref import expon_lr
+    from tclight_b200.postopt import get_expon_lr_func
+
+    N, Bo, epochs = 300, 16, 35
+    total = epochs * N // Bo
+    f = get_expon_lr_func(0.01, 0.001, lr_delay_steps=0, lr_delay_mult=0.0, max_steps=total)
+    assert f(0) == pytest.approx(0.01) and f(total) == pytest.approx(0.001) and f(total + 5) == pytest.approx(0.001)
+    for step in (1, 19, 20, 333, total):
+        assert f(step) == pytest.approx(expon_lr(step, 0.01, 0.001, total), rel=1e-12)
+    # reference quirk (generate.py:394): indices are not strictly monotonic across epochs
+    idx = [ep * N // Bo + i + 1 for ep in range(2) for i in range(math.ceil(N / Bo))]
+    assert idx[18] == 19 and idx[19] == 19
+
+
+def test_config_loader_chain_and_interpolation(tmp_path):
+    from tclight_b200 import config_utils as CU
+
+    base = CU.DEFAULT_YAML
+    child = tmp_path / "droid.yaml"
+    child.write_text(f"work_dir: 'wd/x'\ndata:\n  rgb_path: 'examples/droid.mp4'\n  height: 536\ngeneration:\n  alpha_t: 0.01\n"
+                     f"  frame_range: [0, -1, 1]\n  prompt:\n    droid: an office\nbase_config: {base}\n")
+    cfg = CU.resolve(CU.load_config_file(str(child)))
+    assert cfg.data.height == 536 and cfg.data.width == 960                 # child wins, base fills
+    assert cfg.generation.alpha_t == 0.01 and cfg.generation.n_timesteps == 25
+    assert cfg.inversion.save_path == "wd/x/latents" and cfg.generation.latents_path == "wd/x/latents"
+    assert cfg.generation.output_path == "wd/x"
+    assert cfg.post_opt.epochs == 70 and cfg.post_opt.batch_size == 16
+    assert "float_precision" not in cfg.generation and cfg.float_precision == "fp16"
+    cfg2 = CU.load_config(print_config=False, argv=["--config", str(child), "--multi_axis", "-n", "bad"])
+    assert cfg2.generation.alpha_t == 0.01 and cfg2.generation.negative_prompt == "bad"
+    assert dict(cfg2.generation.prompt) == {"droid": "an office"}
+    CU.save_config(cfg2, str(tmp_path / "out"), gene=True)
+    assert os.path.exists(tmp_path / "out" / "config.yaml")
+
+
+def test_scheduler_coefficients_match_oracle_expressions():
+    from oracle.scheduler_ref import DPMSolverSDEKarras
+    from tclight_b200.scheduler import DPMSolverMultistepSchedulerB200
+
+    ref, mine = DPMSolverSDEKarras(), DPMSolverMultistepSchedulerB200()
+    ref.set_timesteps(25)
+    mine.set_timesteps(25)
+    assert torch.equal(ref.timesteps, mine.timesteps) and torch.equal(ref.sigmas, mine.sigmas)
+    assert len(mine.timesteps) == 25 and float(mine.sigmas[-1]) == 0.0
+    x = torch.randn(2, 4, 4, 4)
+    for i in range(25):
+        c = mine.coefficients(i)
+        assert c["second_order"] == (0 < i < 24)
+        eps = torch.randn(2, 4, 4, 4)
+        x_ref = ref.step(eps, ref.timesteps[i], x, generator=torch.Generator().manual_seed(i))[0]
+        # replay with the scalar coefficients (what the CUDA kernel evaluates)
+        z = torch.randn(2, 4, 4, 4, generator=torch.Generator().manual_seed(i))
+        x0 = (x - c["sigma_c_hat"] * eps) / c["alpha_c_hat"]
+        acc = c["A"] * x + c["B"] * x0 + c["Cn"] * z
+        if c["second_order"]:
+            acc = acc + 0.5 * c["B"] * c["inv_r0"] * (x0 - prev_x0)
+        assert torch.allclose(acc, x_ref, rtol=1e-5, atol=1e-5), i
+        prev_x0 = x0
+        mine.lower_order_nums = min(mine.lower_order_nums + 1, 2)
+        x = x_ref
+    assert torch.allclose(x, prev_x0, atol=1e-6)      # final sigma 0 => x' = x0
+
+
+def test_batch_iterator_matches_dataloader_order():
+    from oracle.postopt_ref import draw_batches
+    from tclight_b200.postopt import batch_iterator
+
+    torch.manual_seed(3)
+    want = draw_batches(37, 16, 3)
+    torch.manual_seed(3)
+    loader = batch_iterator(37, 16)
+    got = [[[int(i) for i in b] for b in loader] for _ in range(3)]
+    assert got == want and [len(b) for b in got[0]] == [16, 16, 5]
+
+
+def test_random_state_dict_has_diffusers_sd15_layout():
+    from tclight_b200.weights import interleave_geglu, pack_conv3x3, random_state_dict
+
+    sd = random_state_dict(block_out_channels=(64, 128, 256, 256))
+    assert sd["conv_in.weight"].shape == (64, 8, 3, 3)
+    assert sd["up_blocks.3.resnets.0.conv1.weight"].shape[1] == 128 + 64
+    assert "down_blocks.3.attentions.0.norm.weight" not in sd and "mid_block.attentions.0.proj_in.weight" in sd
+    w = torch.arange(2 * 3 * 9, dtype=torch.float32).reshape(2, 3, 3, 3)
+    p = pack_conv3x3(w)
+    assert p.shape == (2, 27) and p[1, (1 * 3 + 2) * 3 + 0] == w[1, 0, 1, 2]
+    wi, bi = interleave_geglu(torch.arange(512.)[:, None].repeat(1, 2), torch.arange(512.))
+    assert wi[0, 0] == 0 and wi[128, 0] == 256 and wi[256, 0] == 128 and bi[384] == 384
