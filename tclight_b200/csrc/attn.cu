@@ -7,9 +7,13 @@
 // with the head dim zero-padded to d_pad in {64,128,192} (head_dim 40/80/160) so every tile is
 // a 128-byte-swizzled K-major UMMA operand.
 //
-// Two-pass exact softmax (no accumulator rescaling): pass 1 runs S = Q K^T for every KV tile
-// and keeps only the row max; pass 2 recomputes S, forms P = exp2((S - max) * scale) in
-// registers, stores P as 16-bit into swizzled smem and accumulates O += P V in TMEM.
+// Single-pass online softmax with lazy rescaling: per KV tile S = Q K^T lands in TMEM, the
+// softmax thread that owns a row takes the row max, forms P = exp2(S*scale - m_ref) in registers
+// (m_ref is only advanced when the running max grows by more than 2^8, so P <= 256 and the
+// fp32 accumulator is rescaled rarely), stores P as 16-bit into swizzled smem and the MMA warp
+// accumulates O += P V in TMEM.  The softmax denominator rides along as one extra output column:
+// row `d` of every V^T tile is overwritten with ones in shared memory, so O[:, d] = sum_j P_ij
+// (from the same rounded P as the numerator) and is rescaled together with O.
 // Warp roles: NQ softmax warpgroups (one 128-row Q tile each, ping-pong against the single MMA
 // issuer), one TMA warp, one MMA warp.
 #include "common.cuh"
@@ -110,24 +114,22 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
         for (int c = 0; c < NC; ++c)
           tma_load_3d(smem + OFF_Q + q * QK_TILE + c * 16384, &tm.q, q_full, c * 64, q_row0 + q * 128, bh);
       int kn = 0, vn = 0;
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int j = 0; j < n_kv; ++j) {
-          {
-            const int st = kn % KST;
-            mbar_wait(&k_empty[st], ((kn / KST) & 1) ^ 1);
-            mbar_arrive_expect_tx(&k_full[st], QK_TILE);
-            for (int c = 0; c < NC; ++c)
-              tma_load_3d(smem + OFF_K + st * QK_TILE + c * 16384, &tm.k, &k_full[st], c * 64, j * 128, kv_bh);
-            ++kn;
-          }
-          if (pass == 1) {
-            const int st = vn % VST;
-            mbar_wait(&v_empty[st], ((vn / VST) & 1) ^ 1);
-            mbar_arrive_expect_tx(&v_full[st], V_TILE);
-            for (int c = 0; c < 2; ++c)
-              tma_load_3d(smem + OFF_V + st * V_TILE + c * V_CHUNK, &tm.vt, &v_full[st], j * 128 + c * 64, 0, kv_bh);
-            ++vn;
-          }
+      for (int j = 0; j < n_kv; ++j) {
+        {
+          const int st = kn % KST;
+          mbar_wait(&k_empty[st], ((kn / KST) & 1) ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], QK_TILE);
+          for (int c = 0; c < NC; ++c)
+            tma_load_3d(smem + OFF_K + st * QK_TILE + c * 16384, &tm.k, &k_full[st], c * 64, j * 128, kv_bh);
+          ++kn;
+        }
+        {
+          const int st = vn % VST;
+          mbar_wait(&v_empty[st], ((vn / VST) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], V_TILE);
+          for (int c = 0; c < 2; ++c)
+            tma_load_3d(smem + OFF_V + st * V_TILE + c * V_CHUNK, &tm.vt, &v_full[st], j * 128 + c * 64, 0, kv_bh);
+          ++vn;
         }
       }
     }
@@ -168,14 +170,25 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
 
       mbar_wait(q_full, 0);
       tcgen05_fence_after();
-      // pass 1: scores only
-      for (int j = 0; j < n_kv; ++j) issue_qk_all();
-      // pass 2: scores (one tile ahead) + P V
+      // scores run one tile ahead of P V
       issue_qk_all();
       for (int j = 0; j < n_kv; ++j) {
         if (j + 1 < n_kv) issue_qk_all();
         const int st = vn % VST;
         mbar_wait(&v_full[st], (vn / VST) & 1);
+        {
+          // row `d` of V^T := 1  => O[:, d] accumulates the softmax denominator (swizzle only
+          // permutes 16-byte units inside a 128-byte row, so filling the whole row is layout-safe)
+          const uint32_t one2 = BF16 ? 0x3F803F80u : 0x3C003C00u;
+          const uint4 ones = make_uint4(one2, one2, one2, one2);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint4* rowp = reinterpret_cast<uint4*>(smem + OFF_V + st * V_TILE + c * V_CHUNK + p.d * 128);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) rowp[u] = ones;
+          }
+          fence_proxy_async_smem();
+        }
         tcgen05_fence_after();
         for (int q = 0; q < NQ; ++q) {
           mbar_wait(&p_full[q], pn[q] & 1);
@@ -203,36 +216,10 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const uint32_t t_s = t_lane + q * 128;
     const uint32_t t_o = t_lane + NQ * 128 + q * DPAD;
-    int it = 0;
-    float m = -INFINITY;
-    // ---- pass 1: row max ----
-    for (int j = 0; j < n_kv; ++j, ++it) {
-      mbar_wait(&s_full[q], it & 1);
-      tcgen05_fence_after();
-      const int valid_cols = p.tk - j * 128;
-#pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_s + c0, v);
-        tmem_ld_wait();
-        if (valid_cols >= c0 + 32) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < valid_cols) m = fmaxf(m, __uint_as_float(v[i]));
-        }
-      }
-      tcgen05_fence_before();
-      mbar_arrive(&s_empty[q]);
-    }
-    const float m_s = m * p.scale_log2;
-    float l = 0.f;
+    float m_ref = -INFINITY;                 // reference max (scaled, log2 domain) used by exp2
     uint8_t* p_tile = smem + OFF_P + q * P_TILE;
-    // ---- pass 2: P = exp2(S*scale - m*scale), O += P V ----
-    for (int j = 0; j < n_kv; ++j, ++it) {
-      mbar_wait(&s_full[q], it & 1);
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[q], j & 1);
       tcgen05_fence_after();
       uint32_t s0[32], s1[32], s2[32], s3[32];
       tmem_ld_32x32b_x32(t_s + 0, s0);
@@ -243,17 +230,35 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       tcgen05_fence_before();
       mbar_arrive(&s_empty[q]);
       const int valid_cols = p.tk - j * 128;
+      const bool tail = valid_cols < 128;      // warp-uniform: only the last KV tile
+      if (tail) {
+        auto mask = [&](uint32_t (&s)[32], int c0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i >= valid_cols) s[i] = 0xff800000u;   // -inf
+        };
+        mask(s0, 0); mask(s1, 32); mask(s2, 64); mask(s3, 96);
+      }
+      float mx = -INFINITY;
+      auto rmax = [&](uint32_t (&s)[32]) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+      };
+      rmax(s0); rmax(s1); rmax(s2); rmax(s3);
+      const float m_new = mx * p.scale_log2;
+      float factor = 1.f;
+      if (j == 0) {
+        m_ref = m_new;
+      } else if (m_new > m_ref + 8.f) {
+        factor = fast_exp2(m_ref - m_new);
+        m_ref = m_new;
+      }
       uint32_t pk[64];
       auto do_chunk = [&](uint32_t (&s)[32], int c0) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float e0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_s));
-          float e1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_s));
-          if (valid_cols < 128) {
-            if (c0 + i >= valid_cols) e0 = 0.f;
-            if (c0 + i + 1 >= valid_cols) e1 = 0.f;
-          }
-          l += e0 + e1;
+          const float e0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_ref));
+          const float e1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_ref));
           pk[(c0 + i) >> 1] = E::pack(e0, e1);
         }
       };
@@ -261,8 +266,21 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       do_chunk(s1, 32);
       do_chunk(s2, 64);
       do_chunk(s3, 96);
-      // wait until the previous P V MMA has finished reading this P tile
+      // the previous P V MMA must be done before P (smem) or O (TMEM) are touched
       mbar_wait(&p_empty[q], (j & 1) ^ 1);
+      if (__any_sync(0xffffffffu, factor != 1.f)) {
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < DPAD; c0 += 32) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(t_o + c0, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+          tmem_st_32x32b_x32(t_o + c0, o);
+        }
+        tmem_st_wait();
+      }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint8_t* rowp = p_tile + c * 16384 + row * 128;
@@ -274,13 +292,24 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
         }
       }
       fence_proxy_async_smem();
+      tcgen05_fence_before();
       mbar_arrive(&p_full[q]);
     }
-    // ---- epilogue: O / l ----
+    // ---- epilogue: O[:, :d] / O[:, d] ----
     mbar_wait(o_full, 0);
     tcgen05_fence_after();
     const int t = q_row0 + q * 128 + row;
-    const float inv_l = 1.0f / l;
+    float inv_l;
+    {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(t_o + (p.d & ~15), v);
+      tmem_ld_wait();
+      float l = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i == (p.d & 15)) l = __uint_as_float(v[i]);
+      inv_l = 1.0f / l;
+    }
     typename E::T* out = reinterpret_cast<typename E::T*>(p.out) +
                          (static_cast<long long>(b) * p.tq + t) * p.out_pitch + head * p.d;
 #pragma unroll 1
@@ -336,7 +365,7 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
   TCL_CHECK_ARG(a->q && a->k && a->vt && a->out, "tcl_attention: null pointer");
   TCL_CHECK_ARG(a->dtype == TCL_DTYPE_FP16 || a->dtype == TCL_DTYPE_BF16, "tcl_attention: dtype");
   TCL_CHECK_ARG(a->d_pad == 64 || a->d_pad == 128 || a->d_pad == 192, "tcl_attention: d_pad=%d (64/128/192)", a->d_pad);
-  TCL_CHECK_ARG(a->d > 0 && a->d <= a->d_pad && a->d % 8 == 0, "tcl_attention: d=%d", a->d);
+  TCL_CHECK_ARG(a->d > 0 && a->d < a->d_pad && a->d % 8 == 0, "tcl_attention: d=%d (needs d < d_pad: column d carries the softmax denominator)", a->d);
   TCL_CHECK_ARG(a->batch > 0 && a->heads > 0 && a->tq > 0 && a->tk > 0, "tcl_attention: empty problem");
   TCL_CHECK_ARG(a->kv_batch_div >= 1 && a->batch % a->kv_batch_div == 0, "tcl_attention: kv_batch_div");
   TCL_CHECK_ARG(a->tq_pitch >= a->tq && a->tk_pitch >= a->tk && a->tk_pitch % 8 == 0, "tcl_attention: pitches");
