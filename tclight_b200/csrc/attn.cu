@@ -180,12 +180,12 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
           // row `d` of V^T := 1  => O[:, d] accumulates the softmax denominator (swizzle only
           // permutes 16-byte units inside a 128-byte row, so filling the whole row is layout-safe)
           const uint32_t one2 = BF16 ? 0x3F803F80u : 0x3C003C00u;
-          const uint4 ones = make_uint4(one2, one2, one2, one2);
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            uint4* rowp = reinterpret_cast<uint4*>(smem + OFF_V + st * V_TILE + c * V_CHUNK + p.d * 128);
+            const uint32_t rowa = v_base + st * V_TILE + c * V_CHUNK + p.d * 128;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) rowp[u] = ones;
+            for (int u = 0; u < 8; ++u)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(rowa + u * 16), "r"(one2) : "memory");
           }
           fence_proxy_async_smem();
         }
@@ -217,7 +217,7 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
     const uint32_t t_s = t_lane + q * 128;
     const uint32_t t_o = t_lane + NQ * 128 + q * DPAD;
     float m_ref = -INFINITY;                 // reference max (scaled, log2 domain) used by exp2
-    uint8_t* p_tile = smem + OFF_P + q * P_TILE;
+    const uint32_t p_tile_addr = smem_u32(smem + OFF_P + q * P_TILE);
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[q], j & 1);
       tcgen05_fence_after();
@@ -283,12 +283,14 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint8_t* rowp = p_tile + c * 16384 + row * 128;
+        const uint32_t rowa = p_tile_addr + c * 16384 + row * 128;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int pu = u ^ (row & 7);
-          *reinterpret_cast<uint4*>(rowp + pu * 16) =
-              make_uint4(pk[c * 32 + u * 4 + 0], pk[c * 32 + u * 4 + 1], pk[c * 32 + u * 4 + 2], pk[c * 32 + u * 4 + 3]);
+          // explicit st.shared.v4: a generic-pointer store compiles to ST.E + splits into 32/64-bit pieces
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + pu * 16), "r"(pk[c * 32 + u * 4 + 0]),
+                       "r"(pk[c * 32 + u * 4 + 1]), "r"(pk[c * 32 + u * 4 + 2]), "r"(pk[c * 32 + u * 4 + 3])
+                       : "memory");
         }
       }
       fence_proxy_async_smem();

@@ -91,6 +91,51 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a system-dependent time).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Eight independent non-blocking probes issued back to back (their ~150-clk latencies overlap);
+// bit i of the result = barrier i has completed the phase with parity par[i].
+__device__ __forceinline__ uint32_t mbar_test8(const uint32_t (&addr)[8], const uint32_t (&par)[8]) {
+  uint32_t m;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P0, P1, P2, P3, P4, P5, P6, P7;\n\t"
+      ".reg .b32 t;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P0, [%1], %9;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%2], %10;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P2, [%3], %11;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P3, [%4], %12;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P4, [%5], %13;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P5, [%6], %14;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P6, [%7], %15;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P7, [%8], %16;\n\t"
+      "selp.b32 %0, 1, 0, P0;\n\t"
+      "selp.b32 t, 2, 0, P1;\n\t or.b32 %0, %0, t;\n\t"
+      "selp.b32 t, 4, 0, P2;\n\t or.b32 %0, %0, t;\n\t"
+      "selp.b32 t, 8, 0, P3;\n\t or.b32 %0, %0, t;\n\t"
+      "selp.b32 t, 16, 0, P4;\n\t or.b32 %0, %0, t;\n\t"
+      "selp.b32 t, 32, 0, P5;\n\t or.b32 %0, %0, t;\n\t"
+      "selp.b32 t, 64, 0, P6;\n\t or.b32 %0, %0, t;\n\t"
+      "selp.b32 t, 128, 0, P7;\n\t or.b32 %0, %0, t;\n\t"
+      "}\n"
+      : "=r"(m)
+      : "r"(addr[0]), "r"(addr[1]), "r"(addr[2]), "r"(addr[3]), "r"(addr[4]), "r"(addr[5]), "r"(addr[6]), "r"(addr[7]),
+        "r"(par[0]), "r"(par[1]), "r"(par[2]), "r"(par[3]), "r"(par[4]), "r"(par[5]), "r"(par[6]), "r"(par[7])
+      : "memory");
+  return m;
+}
 // Spin with a watchdog: a broken pipeline traps instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
