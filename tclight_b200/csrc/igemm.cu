@@ -46,6 +46,7 @@ struct IgParams {
   long long out_pitch;        // elements per pixel in out
   float out_scale;
   int vec_ok;                 // out/residual pitches allow 16-byte accesses
+  int tma_store;              // epilogue stages the tile in smem and writes it with TMA (coalesced)
   // head-split modes
   void* sec_ptr[3];
   int sec_vt[3];
@@ -58,6 +59,7 @@ struct IgParams {
 struct IgTmaps {
   CUtensorMap a[TCL_IGEMM_MAX_SRC];
   CUtensorMap b;
+  CUtensorMap c;   // output (TMA-store epilogue): box {32 ch, tw, th, tn}, 64-byte swizzle
 };
 
 __device__ __forceinline__ float gelu_exact(float x) {
@@ -78,7 +80,9 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
   // 1024-byte alignment of the dynamic window is required by the 128B swizzle.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  constexpr uint32_t STAGING_BYTES = BN * 256;     // BN/32 chunks of 128 rows x 64 B (16-bit output tile)
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -90,6 +94,7 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&tm.a[s]);
     tma_prefetch_desc(&tm.b);
+    if (p.tma_store) tma_prefetch_desc(&tm.c);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -190,6 +195,96 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * ACC_STRIDE;
 
+      if (p.tma_store) {
+        // ---- coalesced epilogue: TMEM -> registers -> swizzled smem staging -> TMA store ----
+        constexpr int HALF = BN / 2;
+        const bool geglu = p.mode == TCL_EPI_GEGLU;
+        const int out_cols = geglu ? HALF : BN;
+        const int epi_tid = threadIdx.x - 64;
+        if (epi_tid == 0) bulk_wait_read0();                     // previous tile's stores have read the staging
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const uint32_t stg_row = smem_u32(staging) + row * 64;
+        const int sw = (row >> 1) & 3;
+        const typename E::T* res = (p.residual && valid)
+                                       ? reinterpret_cast<const typename E::T*>(p.residual) + pix * p.res_pitch : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < out_cols; c0 += 32) {
+          uint32_t v[32];
+          uint32_t pk[16];
+          tmem_ld_32x32b_x32(t_row + c0, v);
+          if (geglu) {
+            uint32_t g[32];
+            tmem_ld_32x32b_x32(t_row + HALF + c0, g);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float v0 = __uint_as_float(v[j]), v1 = __uint_as_float(v[j + 1]);
+              float g0 = __uint_as_float(g[j]), g1 = __uint_as_float(g[j + 1]);
+              if (p.bias) {
+                v0 += p.bias[nt * BN + c0 + j];
+                v1 += p.bias[nt * BN + c0 + j + 1];
+                g0 += p.bias[nt * BN + HALF + c0 + j];
+                g1 += p.bias[nt * BN + HALF + c0 + j + 1];
+              }
+              // the reference rounds the projection and gelu(gate) to 16 bit (nn.Linear / F.gelu outputs)
+              v0 = E::to_f(E::from_f(v0)); v1 = E::to_f(E::from_f(v1));
+              g0 = E::to_f(E::from_f(gelu_exact(E::to_f(E::from_f(g0)))));
+              g1 = E::to_f(E::from_f(gelu_exact(E::to_f(E::from_f(g1)))));
+              pk[j / 2] = E::pack(v0 * g0, v1 * g1);
+            }
+          } else {
+            tmem_ld_wait();
+            const int col0 = nt * BN + c0;
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const int col = col0 + g8 * 8;
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g8 * 8 + j]);
+              if (col + 8 <= p.N) {
+                if (p.bias) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+                  const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                }
+                if (res) {
+                  const uint4 r4 = *reinterpret_cast<const uint4*>(res + col);
+                  const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 rf = E::unpack(rr[j]);
+                    f[2 * j] += rf.x;
+                    f[2 * j + 1] += rf.y;
+                  }
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pk[g8 * 4 + j] = E::pack(f[2 * j] * p.out_scale, f[2 * j + 1] * p.out_scale);
+            }
+          }
+          const uint32_t dst = stg_row + (c0 / 32) * 8192;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((u ^ sw) * 16)), "r"(pk[u * 4 + 0]),
+                         "r"(pk[u * 4 + 1]), "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
+                         : "memory");
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);            // accumulator drained: MMA may reuse it
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (epi_tid == 0) {
+          const int x0 = ti_w * p.tw, y0 = ti_h * p.th, img0 = ti_n * p.tn;
+          const int colb = geglu ? nt * HALF : nt * BN;
+          for (int c0 = 0; c0 < out_cols; c0 += 32)
+            if (colb + c0 < (geglu ? p.N / 2 : p.N)) tma_store_4d(&tm.c, smem_u32(staging) + (c0 / 32) * 8192, colb + c0, x0, y0, img0);
+          bulk_commit();
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       if (p.mode == TCL_EPI_GEGLU) {
         // columns [0, BN/2) = value, [BN/2, BN) = gate for the same BN/2 output channels
         constexpr int HALF = BN / 2;
@@ -313,6 +408,7 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store && threadIdx.x == 64) bulk_wait0();   // staging must outlive the last TMA store
   }
 
   tcgen05_fence_before();
@@ -362,7 +458,8 @@ static void choose_tile(int n_img, int h, int w, int* tw_o, int* th_o, int* tn_o
 
 template <int BN, int STAGES, bool BF16>
 static int launch_igemm(const IgTmaps& tm, const IgParams& p, cudaStream_t stream) {
-  constexpr size_t smem = STAGES * (IG_BM * IG_BK * 2 + BN * IG_BK * 2) + 1024 + 256;
+  constexpr size_t smem = STAGES * (IG_BM * IG_BK * 2 + BN * IG_BK * 2) + BN * 256 + 1024 + 256;
+  static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, STAGES, BF16>,
@@ -475,6 +572,17 @@ extern "C" int tcl_igemm(const tcl_igemm_desc* d, cudaStream_t stream) {
                ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) &&
                ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0);
     if (d->mode == TCL_EPI_GEGLU) TCL_CHECK_ARG(p.vec_ok, "tcl_igemm: GEGLU output must be 16-byte aligned with pitch %% 8 == 0");
+    const int n_out = d->mode == TCL_EPI_GEGLU ? d->N / 2 : d->N;
+    p.tma_store = p.vec_ok && (n_out % 8 == 0) && (d->bias == nullptr || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0);
+    if (p.tma_store) {
+      const uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)d->out_w, (uint64_t)d->out_h, (uint64_t)d->n_img};
+      const uint64_t strides[3] = {(uint64_t)d->out_pitch * 2, (uint64_t)d->out_w * d->out_pitch * 2,
+                                   (uint64_t)d->out_h * d->out_w * d->out_pitch * 2};
+      const uint32_t box[4] = {32, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+      const uint32_t estr[4] = {1, 1, 1, 1};
+      int rc = make_tmap(&tm.c, d->out, bf16, 4, dims, strides, box, estr, 64);
+      if (rc) return rc;
+    }
   }
 
 #define TCL_IG_DISPATCH(BN_, ST_)                                            \
@@ -484,7 +592,7 @@ extern "C" int tcl_igemm(const tcl_igemm_desc* d, cudaStream_t stream) {
     case 64: TCL_IG_DISPATCH(64, 8);
     case 128: TCL_IG_DISPATCH(128, 6);
     case 160: TCL_IG_DISPATCH(160, 5);
-    default: TCL_IG_DISPATCH(256, 4);
+    default: TCL_IG_DISPATCH(256, 3);
   }
 #undef TCL_IG_DISPATCH
 }
