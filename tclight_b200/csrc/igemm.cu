@@ -9,7 +9,9 @@
 //               + 2-D box {64, BN} of W per pipeline stage, 128-byte swizzle.
 //   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16 x4 per stage,
 //               fp32 accumulators in TMEM, double buffered (2 x BN columns).
-//   warps 2..5  epilogue: tcgen05.ld -> bias / residual / GEGLU / head-split -> 16-bit stores.
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, interleaved 32-column chunks):
+//               tcgen05.ld -> bias / residual / GEGLU / head-split -> swizzled smem -> TMA store
+//               (or direct 16-bit stores for the head-split layouts).
 #include "common.cuh"
 #include "tmap.h"
 #include "tclight.h"
@@ -18,7 +20,7 @@ namespace tcl {
 
 constexpr int IG_BM = 128;
 constexpr int IG_BK = 64;
-constexpr int IG_THREADS = 192;
+constexpr int IG_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
 
 struct IgSrc {
   int taps;     // 1 or 9
@@ -62,8 +64,19 @@ struct IgTmaps {
   CUtensorMap c;   // output (TMA-store epilogue): box {32 ch, tw, th, tn}, 64-byte swizzle
 };
 
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
+// far below the 16-bit rounding of the result): one reciprocal + one exp2 instead of erff's ~40 instructions.
 __device__ __forceinline__ float gelu_exact(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = exp2f(-z * z * 1.4426950408889634f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  const float erf_x = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_x);
 }
 
 template <int BN, int STAGES, bool BF16>
@@ -101,7 +114,7 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], 8);
     }
     fence_barrier_init();
   }
@@ -175,6 +188,7 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
   } else {
     // ===================== epilogue =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which of the two warps sharing that quarter (takes every other chunk)
     const int row = quarter * 32 + lane;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -202,13 +216,13 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
         const int out_cols = geglu ? HALF : BN;
         const int epi_tid = threadIdx.x - 64;
         if (epi_tid == 0) bulk_wait_read0();                     // previous tile's stores have read the staging
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const uint32_t stg_row = smem_u32(staging) + row * 64;
         const int sw = (row >> 1) & 3;
         const typename E::T* res = (p.residual && valid)
                                        ? reinterpret_cast<const typename E::T*>(p.residual) + pix * p.res_pitch : nullptr;
 #pragma unroll 1
-        for (int c0 = 0; c0 < out_cols; c0 += 32) {
+        for (int c0 = half * 32; c0 < out_cols; c0 += 64) {
           uint32_t v[32];
           uint32_t pk[16];
           tmem_ld_32x32b_x32(t_row + c0, v);
@@ -233,31 +247,33 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
               pk[j / 2] = E::pack(v0 * g0, v1 * g1);
             }
           } else {
-            tmem_ld_wait();
+            // bias / residual loads are issued before waiting on the TMEM load so their latencies overlap
             const int col0 = nt * BN + c0;
+            float4 bb[8];
+            uint4 rr4[4];
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
               const int col = col0 + g8 * 8;
+              const bool in = col + 8 <= p.N;
+              bb[2 * g8] = (p.bias && in) ? *reinterpret_cast<const float4*>(p.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+              bb[2 * g8 + 1] = (p.bias && in) ? *reinterpret_cast<const float4*>(p.bias + col + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              rr4[g8] = (res && in) ? *reinterpret_cast<const uint4*>(res + col) : make_uint4(0, 0, 0, 0);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
               float f[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g8 * 8 + j]);
-              if (col + 8 <= p.N) {
-                if (p.bias) {
-                  const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-                  const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                }
-                if (res) {
-                  const uint4 r4 = *reinterpret_cast<const uint4*>(res + col);
-                  const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+              const float4 b0 = bb[2 * g8], b1 = bb[2 * g8 + 1];
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              const uint32_t rr[4] = {rr4[g8].x, rr4[g8].y, rr4[g8].z, rr4[g8].w};
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 rf = E::unpack(rr[j]);
-                    f[2 * j] += rf.x;
-                    f[2 * j + 1] += rf.y;
-                  }
-                }
+              for (int j = 0; j < 4; ++j) {
+                const float2 rf = E::unpack(rr[j]);
+                f[2 * j] += rf.x;
+                f[2 * j + 1] += rf.y;
               }
 #pragma unroll
               for (int j = 0; j < 4; ++j) pk[g8 * 4 + j] = E::pack(f[2 * j] * p.out_scale, f[2 * j + 1] * p.out_scale);
@@ -274,7 +290,7 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);            // accumulator drained: MMA may reuse it
         fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (epi_tid == 0) {
           const int x0 = ti_w * p.tw, y0 = ti_h * p.th, img0 = ti_n * p.tn;
           const int colb = geglu ? nt * HALF : nt * BN;
@@ -290,7 +306,7 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
         constexpr int HALF = BN / 2;
         typename E::T* out = reinterpret_cast<typename E::T*>(p.out);
 #pragma unroll 1
-        for (int c0 = 0; c0 < HALF; c0 += 16) {
+        for (int c0 = half * 16; c0 < HALF; c0 += 32) {
           uint32_t v[16], g[16];
           tmem_ld_32x32b_x16(t_row + c0, v);
           tmem_ld_32x32b_x16(t_row + HALF + c0, g);
@@ -320,7 +336,7 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
         }
       } else {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_row + c0, v);
           tmem_ld_wait();
