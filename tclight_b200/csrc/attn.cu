@@ -22,6 +22,10 @@
 
 namespace tcl {
 
+#ifndef TCL_ATTN_POLY
+#define TCL_ATTN_POLY 0   // of every 8 exponentials, how many run as FMA-pipe polynomials (see poly_exp2)
+#endif
+
 struct AttnParams {
   int tq, tk;          // valid query / key rows per (batch, head)
   int heads, d;        // true head dim
@@ -40,6 +44,28 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// exp2 on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], 2^f by a minimax
+// polynomial (degree 3: rel. error 1.0e-4 for bf16 P; degree 4: 3.5e-6 for fp16 P), exponent added as
+// integer.  Valid for -126 <= x <= ~100; callers pass x <= 8.
+template <bool BF16>
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;          // 1.5 * 2^23: the low mantissa bits now hold round(x)
+  const float f = x - (t - 12582912.f);
+  float pl;
+  if (BF16) {
+    pl = fmaf(0.055838283f, f, 0.24263948f);
+    pl = fmaf(pl, f, 0.69313675f);
+    pl = fmaf(pl, f, 0.99992454f);
+  } else {
+    pl = fmaf(0.009666368f, f, 0.055921976f);
+    pl = fmaf(pl, f, 0.2402235f);
+    pl = fmaf(pl, f, 0.693121f);
+    pl = fmaf(pl, f, 1.0f);
+  }
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
 }
 
 template <int NQ, int DPAD, int KST, int VST, bool BF16>
@@ -226,6 +252,9 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       tmem_ld_32x32b_x32(t_s + 32, s1);
       tmem_ld_32x32b_x32(t_s + 64, s2);
       tmem_ld_32x32b_x32(t_s + 96, s3);
+      // the previous P V MMA must be done before P (smem) or O (TMEM) are touched; checking here hides the
+      // barrier round trip behind the TMEM load
+      mbar_wait(&p_empty[q], (j & 1) ^ 1);
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(&s_empty[q]);
@@ -239,12 +268,16 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
         };
         mask(s0, 0); mask(s1, 32); mask(s2, 64); mask(s3, 96);
       }
-      float mx = -INFINITY;
-      auto rmax = [&](uint32_t (&s)[32]) {
+      // four independent max chains (a single 128-long dependent chain costs ~500 clk)
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-      };
-      rmax(s0); rmax(s1); rmax(s2); rmax(s3);
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
+        mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
+        mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       const float m_new = mx * p.scale_log2;
       float factor = 1.f;
       if (j == 0) {
@@ -253,12 +286,16 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
         factor = fast_exp2(m_ref - m_new);
         m_ref = m_new;
       }
+      // 3 of every 8 exponentials run as polynomials on the FMA pipe, 5 on MUFU.EX2 (16 lanes/clk/SM is the
+      // binding pipe of this kernel; the split balances the two pipes)
       uint32_t pk[64];
       auto do_chunk = [&](uint32_t (&s)[32], int c0) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float e0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_ref));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_ref));
+          const float a0 = fmaf(__uint_as_float(s[i]), p.scale_log2, -m_ref);
+          const float a1 = fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_ref);
+          const float e0 = ((i & 7) < TCL_ATTN_POLY) ? poly_exp2<BF16>(a0) : fast_exp2(a0);
+          const float e1 = (((i + 1) & 7) < TCL_ATTN_POLY) ? poly_exp2<BF16>(a1) : fast_exp2(a1);
           pk[(c0 + i) >> 1] = E::pack(e0, e1);
         }
       };
@@ -266,8 +303,6 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       do_chunk(s1, 32);
       do_chunk(s2, 64);
       do_chunk(s3, 96);
-      // the previous P V MMA must be done before P (smem) or O (TMEM) are touched
-      mbar_wait(&p_empty[q], (j & 1) ^ 1);
       if (__any_sync(0xffffffffu, factor != 1.f)) {
         tcgen05_fence_after();
 #pragma unroll 1
