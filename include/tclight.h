@@ -219,6 +219,9 @@ typedef struct {
                               [N,3,tcl_postopt_pyramid_elems(H,W)]                           */
   float lambda_dssim, lambda_flow, lambda_tv;
   int32_t max_batch;       /* largest n_batch that will be used with this workspace          */
+  int32_t norm_batch;      /* data parallel: GLOBAL batch size the loss means are taken over
+                              (0 = the call's own batch)                                     */
+  int32_t norm_valid;      /* data parallel: GLOBAL number of batch frames with index > 0    */
   void* workspace;         /* >= tcl_postopt_workspace_bytes(H, W, max_batch), ZERO-FILLED once
                               by the caller before the first iteration                        */
   size_t workspace_bytes;
@@ -233,6 +236,15 @@ int tcl_uvt_iteration(const tcl_postopt_ctx* ctx, const int* idx_host, int n_bat
 int tcl_exposure_iteration(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, float* exposure, float* grad,
                            float* m, float* v, float lr, float beta1, float beta2, float eps, int step,
                            float* loss_out, tcl_stream_t stream);
+/* Data-parallel split of the two calls above (each rank takes a slice of the batch, the
+ * [U,3] / [N,12] gradients are all-reduced, every rank applies the same Adam step): gradient accumulation
+ * only (loss_out = this rank's additive share of {loss, flow, photometric}), then tcl_adam_step. */
+int tcl_uvt_gradient(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, const int* ids, long long U,
+                     const float* fdc, float* grad, float* loss_out, tcl_stream_t stream);
+int tcl_exposure_gradient(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, const float* exposure, float* grad,
+                          float* loss_out, tcl_stream_t stream);
+int tcl_adam_step(float* p, float* grad, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                  int step, tcl_stream_t stream);
 /* generate.py:477-479: fdc = RGB2SH(scatter_mean(edited, unq_inv)); cnt_ws = U floats of scratch */
 int tcl_uvt_init(const float* edited, const int* ids, int N, int H, int W, long long U, float* fdc, float* cnt_ws,
                  tcl_stream_t stream);

@@ -205,7 +205,7 @@ class PostoptCtx(C.Structure):
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("edited", C.c_void_p), ("past_flows", C.c_void_p), ("mask_bwd", C.c_void_p), ("ypyr", C.c_void_p),
         ("lambda_dssim", C.c_float), ("lambda_flow", C.c_float), ("lambda_tv", C.c_float),
-        ("max_batch", C.c_int32),
+        ("max_batch", C.c_int32), ("norm_batch", C.c_int32), ("norm_valid", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
@@ -234,3 +234,13 @@ lib.tcl_exposure_bake.restype = C.c_int
 lib.tcl_debug_ssim_level.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_void_p]
 lib.tcl_debug_ssim_level.restype = C.c_int
+
+lib.tcl_uvt_gradient.argtypes = [C.POINTER(PostoptCtx), C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]
+lib.tcl_uvt_gradient.restype = C.c_int
+lib.tcl_exposure_gradient.argtypes = [C.POINTER(PostoptCtx), C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]
+lib.tcl_exposure_gradient.restype = C.c_int
+lib.tcl_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float,
+                              C.c_float, C.c_int, C.c_void_p]
+lib.tcl_adam_step.restype = C.c_int

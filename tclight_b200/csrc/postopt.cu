@@ -581,6 +581,7 @@ struct LossAsm {
   float* scal; float* loss_out;     // loss_out[0..2] = total, flow, photometric
   float inv_flow_cnt, inv_tv_h, inv_tv_w, inv_l1_cnt;
   float lambda_flow, lambda_dssim, lambda_tv_over_n;
+  float ms_share;                    // local planes / global planes (1 on a single GPU)
   int stage;                         // 1 or 2
 };
 
@@ -601,9 +602,9 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
     const float ms = la.scal[SC_MSSSIM];
     float photo, tv = 0.f;
     if (la.stage == 1) {
-      photo = la.scal[SC_L1] * la.inv_l1_cnt * (1.f - la.lambda_dssim) + (1.f - ms) * la.lambda_dssim;
+      photo = la.scal[SC_L1] * la.inv_l1_cnt * (1.f - la.lambda_dssim) + la.ms_share * (1.f - ms) * la.lambda_dssim;
     } else {
-      photo = (1.f - ms) * la.lambda_dssim;
+      photo = la.ms_share * (1.f - ms) * la.lambda_dssim;
       tv = la.lambda_tv_over_n * 2.f * (la.scal[SC_TV_H] * la.inv_tv_h + la.scal[SC_TV_W] * la.inv_tv_w);
     }
     la.loss_out[0] = (1.f - la.lambda_flow) * photo + la.lambda_flow * flow + tv;
@@ -745,12 +746,16 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
                          const int* ids, long long U, float* fdc, float* grad, float* m, float* v,
                          // stage 1
                          float* expo, float* egrad, float* em, float* ev,
-                         float lr, float beta1, float beta2, float eps, int step, float* loss_out, cudaStream_t stream) {
+                         float lr, float beta1, float beta2, float eps, int step, float* loss_out, cudaStream_t stream,
+                         bool do_adam = true) {
   TCL_CHECK_ARG(c && idx_host && nb > 0 && nb <= MAXB, "postopt: batch size %d (max %d)", nb, MAXB);
   TCL_CHECK_ARG(c->edited && c->past_flows && c->mask_bwd && c->ypyr && c->workspace, "postopt: null context pointer");
   TCL_CHECK_ARG(c->max_batch >= nb && c->max_batch <= MAXB, "postopt: batch %d exceeds ctx.max_batch %d", nb, c->max_batch);
   TCL_CHECK_ARG(c->workspace_bytes >= ws_bytes(c->H, c->W, c->max_batch), "postopt: workspace too small");
-  TCL_CHECK_ARG(step >= 1, "postopt: Adam step must start at 1");
+  TCL_CHECK_ARG(step >= 1 || !do_adam, "postopt: Adam step must start at 1");
+  // data-parallel normalisers: means are over the GLOBAL batch; 0 = this call is the whole batch
+  const int nb_g = c->norm_batch > 0 ? c->norm_batch : nb;
+  TCL_CHECK_ARG(nb_g >= nb, "postopt: norm_batch %d < local batch %d", nb_g, nb);
   int rc = ensure_gauss();
   if (rc) return rc;
   const int H = c->H, W = c->W;
@@ -791,7 +796,8 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
     TCL_CHECK_LAUNCH("postopt(ssim_fwd)");
   }
   // 4. loss head
-  const float k_ms = -(1.f - c->lambda_flow) * c->lambda_dssim / (float)planes;
+  const int planes_g = nb_g * 3;
+  const float k_ms = -(1.f - c->lambda_flow) * c->lambda_dssim / (float)planes_g;
   msssim_head_kernel<<<1, 64, 0, stream>>>(w.sums, planes, py, k_ms, w.coef, w.scal);
   TCL_CHECK_LAUNCH("postopt(head)");
   // 5. SSIM backward 4 -> 1
@@ -816,11 +822,12 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
   memset(&q, 0, sizeof(q));
   q.H = H; q.W = W; q.P = P; q.bt = bt; q.X = w.X; q.flags = w.flags; q.flows = c->past_flows; q.mask = c->mask_bwd;
   q.d1 = w.dpyr + py.off[1]; q.d1_stride = py.total; q.h1 = py.h[1]; q.w1 = py.w[1]; q.ph0 = py.ph[0]; q.pw0 = py.pw[0];
-  const float flow_cnt = (float)n_valid * 3.f * (float)P;
-  q.k_flow = n_valid > 0 ? c->lambda_flow / flow_cnt : 0.f;
+  const int n_valid_g = c->norm_batch > 0 ? c->norm_valid : n_valid;
+  const float flow_cnt = (float)n_valid_g * 3.f * (float)P;
+  q.k_flow = n_valid_g > 0 ? c->lambda_flow / flow_cnt : 0.f;
   const float count_h = 3.f * (float)(H - 1) * (float)W, count_w = 3.f * (float)H * (float)(W - 1);
-  if (stage == 2) { q.k_tvh = c->lambda_tv * 2.f / (count_h * nb); q.k_tvw = c->lambda_tv * 2.f / (count_w * nb); }
-  q.k_l1 = stage == 1 ? (1.f - c->lambda_flow) * (1.f - c->lambda_dssim) / ((float)planes * (float)P) : 0.f;
+  if (stage == 2) { q.k_tvh = c->lambda_tv * 2.f / (count_h * nb_g); q.k_tvw = c->lambda_tv * 2.f / (count_w * nb_g); }
+  q.k_l1 = stage == 1 ? (1.f - c->lambda_flow) * (1.f - c->lambda_dssim) / ((float)planes_g * (float)P) : 0.f;
   q.edited = c->edited; q.G_pre = w.G_pre; q.scal = w.scal; q.ids = ids; q.grad_fdc = grad; q.grad_expo = egrad;
   dim3 g0(gridp(P, 256, 148 * 2), nb);
   if (stage == 2) level0_kernel<0><<<g0, 256, 0, stream>>>(q); else level0_kernel<1><<<g0, 256, 0, stream>>>(q);
@@ -830,12 +837,17 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
   // 7. Adam (+ loss assembly)
   LossAsm la;
   la.scal = w.scal; la.loss_out = loss_out;
-  la.inv_flow_cnt = n_valid > 0 ? 1.f / flow_cnt : NAN;   // mean over an empty selection is NaN in the reference
-  la.inv_tv_h = 1.f / count_h; la.inv_tv_w = 1.f / count_w; la.inv_l1_cnt = 1.f / ((float)planes * (float)P);
-  la.lambda_flow = c->lambda_flow; la.lambda_dssim = c->lambda_dssim; la.lambda_tv_over_n = c->lambda_tv / nb; la.stage = stage;
+  la.inv_flow_cnt = n_valid_g > 0 ? 1.f / flow_cnt : NAN;   // mean over an empty selection is NaN in the reference
+  la.inv_tv_h = 1.f / count_h; la.inv_tv_w = 1.f / count_w; la.inv_l1_cnt = 1.f / ((float)planes_g * (float)P);
+  la.lambda_flow = c->lambda_flow; la.lambda_dssim = c->lambda_dssim; la.lambda_tv_over_n = c->lambda_tv / nb_g; la.stage = stage;
+  la.ms_share = (float)planes / (float)planes_g;
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
-  if (stage == 2) adam_kernel<<<gridp(U * 3, 256, 148 * 16), 256, 0, stream>>>(fdc, grad, m, v, U * 3, lr, beta1, beta2, eps, bc1, bc2_sqrt, la);
+  if (!do_adam) {
+    // gradient only (data parallel: the caller all-reduces grad, then calls tcl_adam_step): n = 0 elements,
+    // the single block just assembles this rank's share of the loss
+    adam_kernel<<<1, 32, 0, stream>>>(nullptr, nullptr, nullptr, nullptr, 0, 0.f, beta1, beta2, eps, 1.f, 1.f, la);
+  } else if (stage == 2) adam_kernel<<<gridp(U * 3, 256, 148 * 16), 256, 0, stream>>>(fdc, grad, m, v, U * 3, lr, beta1, beta2, eps, bc1, bc2_sqrt, la);
   else adam_kernel<<<gridp((long long)c->N * 12, 256), 256, 0, stream>>>(expo, egrad, em, ev, (long long)c->N * 12, lr, beta1, beta2, eps, bc1, bc2_sqrt, la);
   TCL_CHECK_LAUNCH("postopt(adam)");
   return TCL_OK;
@@ -912,5 +924,32 @@ extern "C" int tcl_debug_ssim_level(const float* X, const float* Y, int planes, 
     ssim_bwd_kernel<<<grid, 256, bwd_smem, stream>>>(X, hw, Y, 3 * hw, hw, bt, h, w, C1, C2, coef, use_ssim, nullptr, 0, 0, 0, 0, 0, dX, hw);
     TCL_CHECK_LAUNCH("tcl_debug_ssim_level(bwd)");
   }
+  return TCL_OK;
+}
+
+// ---- data-parallel variants: gradient accumulation only, then a separate Adam step ----
+extern "C" int tcl_uvt_gradient(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, const int* ids, long long U,
+                                const float* fdc, float* grad, float* loss_out, cudaStream_t stream) {
+  TCL_CHECK_ARG(ids && fdc && grad && U > 0, "tcl_uvt_gradient: null pointer");
+  return run_iteration(2, ctx, idx_host, n_batch, ids, U, const_cast<float*>(fdc), grad, nullptr, nullptr, nullptr, nullptr, nullptr,
+                       nullptr, 0.f, 0.9f, 0.999f, 1e-15f, 1, loss_out, stream, false);
+}
+
+extern "C" int tcl_exposure_gradient(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, const float* exposure, float* grad,
+                                     float* loss_out, cudaStream_t stream) {
+  TCL_CHECK_ARG(exposure && grad, "tcl_exposure_gradient: null pointer");
+  return run_iteration(1, ctx, idx_host, n_batch, nullptr, 0, nullptr, nullptr, nullptr, nullptr, const_cast<float*>(exposure), grad,
+                       nullptr, nullptr, 0.f, 0.9f, 0.999f, 1e-8f, 1, loss_out, stream, false);
+}
+
+extern "C" int tcl_adam_step(float* p, float* grad, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                             int step, cudaStream_t stream) {
+  TCL_CHECK_ARG(p && grad && m && v && n > 0 && step >= 1, "tcl_adam_step: args");
+  LossAsm la;
+  memset(&la, 0, sizeof(la));
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  adam_kernel<<<gridp(n, 256, 148 * 16), 256, 0, stream>>>(p, grad, m, v, n, lr, beta1, beta2, eps, bc1, bc2_sqrt, la);
+  TCL_CHECK_LAUNCH("tcl_adam_step");
   return TCL_OK;
 }

@@ -102,6 +102,42 @@ class _Context:
         self.c = c
 
 
+def _shard_info(gen):
+    """(rank, world) when the optimiser runs data parallel (Generator.set_shard + an initialised process group)."""
+    world = int(getattr(gen, "_world", 1))
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise TclError("set_shard(world > 1) needs an initialised torch.distributed process group")
+        return int(getattr(gen, "_rank", 0)), world
+    return 0, 1
+
+
+def shard_batch(idxs, rank: int, world: int):
+    """This rank's slice of a batch (round robin) plus the global normalisers: every rank draws the same
+    batches (same CPU RNG seed), processes idxs[rank::world], and the loss means stay global."""
+    lst = [int(i) for i in idxs]
+    return lst[rank::world], len(lst), sum(1 for i in lst if i > 0)
+
+
+def _dp_iteration(stage, ctx, mine, n_global, n_valid_global, params, grad, m, v, ids, U, lr, eps, step, loss_row):
+    """Gradient on the local slice with global normalisers -> all-reduce -> identical Adam on every rank."""
+    import torch.distributed as dist
+
+    ctx.c.norm_batch, ctx.c.norm_valid = n_global, n_valid_global
+    if mine:
+        arr, nb = _idx_array(mine)
+        if stage == 2:
+            check(lib.tcl_uvt_gradient(C.byref(ctx.c), arr, nb, ids.data_ptr(), U, params.data_ptr(), grad.data_ptr(),
+                                       loss_row.data_ptr(), stream_ptr()), "tcl_uvt_gradient")
+        else:
+            check(lib.tcl_exposure_gradient(C.byref(ctx.c), arr, nb, params.data_ptr(), grad.data_ptr(), loss_row.data_ptr(),
+                                            stream_ptr()), "tcl_exposure_gradient")
+    dist.all_reduce(grad)
+    check(lib.tcl_adam_step(params.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), params.numel(), lr, 0.9, 0.999, eps,
+                            step, stream_ptr()), "tcl_adam_step")
+
+
 def _idx_array(idxs) -> Tuple[C.Array, int]:
     lst = [int(i) for i in idxs]
     return (C.c_int * len(lst))(*lst), len(lst)
@@ -114,6 +150,7 @@ def exposure_align(gen) -> Tuple[torch.Tensor, List[float]]:
     Bo = gen.opt_batch_size
     dev = ds.edited_images.device
     total_iters = gen.epochs_exposure * N // Bo
+    rank, world = _shard_info(gen)
     ctx = _Context(ds, gen.lambda_dssim, gen.lambda_flow, gen.lambda_tv, Bo)
     exposure = torch.eye(3, 4, device=dev)[None].repeat(N, 1, 1).contiguous()
     grad, m, v = (torch.zeros_like(exposure) for _ in range(3))
@@ -127,11 +164,18 @@ def exposure_align(gen) -> Tuple[torch.Tensor, List[float]]:
         for i, idxs in enumerate(loader):
             iter_idx = epoch * N // Bo + i + 1                     # generate.py:394
             lr = float(lr_fn(iter_idx))
-            arr, nb = _idx_array(idxs)
             step += 1
+            if world > 1:
+                mine, ng, nv = shard_batch(idxs, rank, world)
+                _dp_iteration(1, ctx, mine, ng, nv, exposure, grad, m, v, None, 0, lr, 1e-8, step, losses[step - 1])
+                continue
+            arr, nb = _idx_array(idxs)
             check(lib.tcl_exposure_iteration(C.byref(ctx.c), arr, nb, exposure.data_ptr(), grad.data_ptr(), m.data_ptr(),
                                              v.data_ptr(), lr, 0.9, 0.999, 1e-8, step, losses[step - 1].data_ptr(), stream_ptr()),
                   "tcl_exposure_iteration")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(losses)          # per-rank loss shares are additive
     gen._exposure = exposure
     ds.exposure_align(exposure)                                     # generate.py:449
     return ds.edited_images, losses[:step, 0].tolist()
@@ -153,6 +197,7 @@ def unique_tensor_optimization(gen) -> Tuple[torch.Tensor, List[float]]:
     ids = unq.to(device=dev, dtype=torch.int32).contiguous()
     U = int(unq.max().item()) + 1
     feature_lr = gen.feature_lr * Bo / N                           # generate.py:474
+    rank, world = _shard_info(gen)
     ctx = _Context(ds, gen.lambda_dssim, gen.lambda_flow, gen.lambda_tv, Bo)
     fdc = torch.empty((U, 3), device=dev, dtype=torch.float32)
     cnt = torch.empty(U, device=dev, dtype=torch.float32)
@@ -166,11 +211,18 @@ def unique_tensor_optimization(gen) -> Tuple[torch.Tensor, List[float]]:
     loader = batch_iterator(N, Bo)
     for epoch in range(gen.epochs):
         for idxs in loader:
-            arr, nb = _idx_array(idxs)
             step += 1
+            if world > 1:
+                mine, ng, nv = shard_batch(idxs, rank, world)
+                _dp_iteration(2, ctx, mine, ng, nv, fdc, grad, m, v, ids, U, feature_lr, 1e-15, step, losses[step - 1])
+                continue
+            arr, nb = _idx_array(idxs)
             check(lib.tcl_uvt_iteration(C.byref(ctx.c), arr, nb, ids.data_ptr(), U, fdc.data_ptr(), grad.data_ptr(), m.data_ptr(),
                                         v.data_ptr(), feature_lr, 0.9, 0.999, 1e-15, step, losses[step - 1].data_ptr(), stream_ptr()),
                   "tcl_uvt_iteration")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(losses)
     images = torch.empty((N, 3, H, W), device=dev, dtype=torch.float32)
     check(lib.tcl_uvt_render(fdc.data_ptr(), ids.data_ptr(), N, H, W, images.data_ptr(), stream_ptr()), "tcl_uvt_render")
     gen._features_dc = fdc
