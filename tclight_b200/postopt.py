@@ -294,20 +294,36 @@ def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: i
 
     def run(k, step0):
         for i in range(k):
-            idxs = torch.randperm(N, generator=gcpu)[:Bo].tolist()
+            idxs = torch.randperm(N, generator=gcpu)[:Bo].tolist()      # same seed => same batches on every rank
+            row = losses[(step0 + i) % len(losses)]
+            if world > 1:
+                mine, ng, nv = shard_batch(idxs, rank, world)
+                _dp_iteration(2, ctx, mine, ng, nv, fdc, grad, m, v, ids, U, lr, 1e-15, step0 + i + 1, row)
+                continue
             arr, nb = _idx_array(idxs)
             check(lib.tcl_uvt_iteration(C.byref(ctx.c), arr, nb, ids.data_ptr(), U, fdc.data_ptr(), grad.data_ptr(), m.data_ptr(),
-                                        v.data_ptr(), lr, 0.9, 0.999, 1e-15, step0 + i + 1, losses[(step0 + i) % len(losses)].data_ptr(),
-                                        stream_ptr()), "tcl_uvt_iteration")
+                                        v.data_ptr(), lr, 0.9, 0.999, 1e-15, step0 + i + 1, row.data_ptr(), stream_ptr()),
+                  "tcl_uvt_iteration")
+
+    def sync():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
 
     run(3, 0)
-    torch.cuda.synchronize()
+    sync()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     run(iters, 3)
     e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / iters
+    sync()
+    ms_t = torch.tensor([s.elapsed_time(e) / iters], device=device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(losses)
+    ms = ms_t.item()
     P_ = H * W
     alg_bytes = 80.0 * Bo * P_ + 84.0 * U
     try:
@@ -320,7 +336,8 @@ def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: i
     return {"metric": "stage2_iters_per_sec", "value": 1e3 / ms, "unit": "it/s", "ms_per_iter": ms, "frames": N, "batch": Bo,
             "U": U, "U_over_NP": U / (N * P_), "algorithmic_bytes_per_iter": alg_bytes,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": kind, "unit": "GB/s", "frac": ach / peak, "traffic": None},
-            "loss_first_last": [losses[3, 0].item(), losses[(3 + iters - 1) % len(losses), 0].item()], "n_gpus": 1,
+            "loss_first_last": [losses[3, 0].item(), losses[(3 + iters - 1) % len(losses), 0].item()], "n_gpus": world,
+            "parallelism": f"batch-parallel x{world}, NCCL all-reduce of the [U,3] gradient" if world > 1 else "single GPU",
             "note": "dense-Adam semantics (every UVT row updated every iteration, as torch.optim.Adam does)"}
 
 
