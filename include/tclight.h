@@ -93,7 +93,8 @@ int tcl_igemm(const tcl_igemm_desc* desc, tcl_stream_t stream);
  * (TCL_EPI_HEADS): q [batch*heads, tq_pitch, d_pad], k [kv_batch*heads, tk_pitch, d_pad],
  * vt [kv_batch*heads, d_pad, tk_pitch], zero padded beyond d.  kv_batch = batch/kv_batch_div
  * (cross-attention: every frame of a CFG half shares one text embedding, generate.py:295).
- * out is token-major [batch, tq, heads*d].  Softmax is exact (two passes), scale 1/sqrt(d).
+ * out is token-major [batch, tq, heads*d].  Single-pass online softmax (fp32 statistics, P rounded to the
+ * 16-bit type before P V as in flash attention), scale 1/sqrt(d).
  */
 typedef struct {
   int32_t dtype;
@@ -109,6 +110,9 @@ typedef struct {
 } tcl_attn_desc;
 
 int tcl_attention(const tcl_attn_desc* desc, tcl_stream_t stream);
+/* tuning hook: kernel variant used by tcl_attention (0 = P staged through shared memory, >= 1 = P handed to the
+ * P V MMA through tensor memory, with different exp2 / warpgroup-stagger settings); returns the previous value */
+int tcl_debug_attention_variant(int variant);
 
 /* ---- normalisation / staging (HBM-bound) --------------------------------------------------
  * GroupNorm(+SiLU) of diffusers ResnetBlock2D / Transformer2DModel / conv_norm_out over NHWC,
@@ -165,6 +169,13 @@ int tcl_scale_inplace(int latent_dtype, void* x, long long n, float s, tcl_strea
 int tcl_dpm_step(int latent_dtype, const void* eps, const void* x, const void* x0_prev, const float* z,
                  void* x0_out, void* x_out, long long n, float sigma_c_hat, float alpha_c_hat, float A, float B,
                  float Cn, float inv_r0, int second_order, tcl_stream_t stream);
+
+/* DDIM step in either direction (invert.py:215-244 Inverter.pred_next_x):
+ *   x_out = mu_out * ((x - sig_in * eps) / mu_in) + sig_out * eps
+ * inversion: (mu_in, sig_in) = (sqrt(a_prev), sqrt(1-a_prev)), (mu_out, sig_out) = (sqrt(a_t), sqrt(1-a_t));
+ * sampling: the two pairs swapped.  Each tensor op rounds to the latent dtype like the reference expression. */
+int tcl_ddim_next(int latent_dtype, const void* eps, const void* x, void* x_out, long long n, float mu_in, float sig_in,
+                  float mu_out, float sig_out, tcl_stream_t stream);
 
 /* ---- VidToMe token merging ------------------------------------------------------------------
  * bipartite_soft_matching_randframe (utils/VidToMe/vidtome/merge.py:20-159) and
@@ -252,6 +263,37 @@ int tcl_uvt_init(const float* edited, const int* ids, int N, int H, int W, long 
 int tcl_uvt_render(const float* fdc, const int* ids, int N, int H, int W, float* out, tcl_stream_t stream);
 /* OptDataset.exposure_align (utils/dataloader.py:38-42): edited <- clamp(edited x E[:3,:3] + E[:,3]) in place */
 int tcl_exposure_bake(float* edited, const float* exposure, int N, int H, int W, tcl_stream_t stream);
+
+/* ---- stage-2 producers (HBM-bound, fp32 / int32) -------------------------
+ * warp_bicubic   : warp_flow (utils/flow_utils.py:5-16): out[n,c,y,x] = bicubic sample of frames[n,c] at
+ *                  (x + flows[n,0,y,x], y + flows[n,1,y,x]), zeros padding, align_corners=True.
+ * max_f32        : out[0] = max(x) on the device (feeds the thresholds below without a host sync;
+ *                  flow_utils.py:52, 71 call .max().item()).
+ * soft_mask_bwd  : get_soft_mask_bwds (flow_utils.py:40-54): out [N,1,H,W]; frame 0 = 1, frame i =
+ *                  sigmoid(-beta*(|past_i + W(flow_{i-1})| - (|past_i| + |W(flow_{i-1})| + 1)*alpha))
+ *                  * sigmoid(-beta*(max_c|W(img_{i-1}) - img_i| - images_max*diff_threshold)), W = warp by past_i.
+ * flow_ids       : get_flowid (flow_utils.py:56-92): ids [N,H,W] int32.  A pixel of frame i inherits the id of
+ *                  the frame i-1 pixel whose rounded forward flow lands on it (valid if in bounds,
+ *                  mask_bwds[i] > 0.5 at the source, max_c|frames_i(target) - frames_{i-1}(source)| <
+ *                  frames_max*rgb_threshold; several candidates: the largest source index wins = the
+ *                  reference's CPU result); all other pixels get fresh consecutive ids in frame-major /
+ *                  row-major order.  num_ids (device int64, may be NULL) receives the id count U.
+ * unique_inverse : voxelization(voxel_size=None) (utils/general_utils.py:223-233) =
+ *                  torch.unique(ids[:,None], dim=0, return_inverse=True)[1] for ids in [0, id_range):
+ *                  inverse[i] = rank of ids[i] among the distinct ids (int64 like torch), num_unique = U.
+ */
+int tcl_warp_bicubic(const float* frames, const float* flows, int N, int C, int H, int W, float* out,
+                     tcl_stream_t stream);
+int tcl_max_f32(const float* x, long long n, float* out, tcl_stream_t stream);
+int tcl_soft_mask_bwd(const float* images, const float* flows, const float* past_flows, int N, int H, int W, float alpha,
+                      float beta, double diff_threshold, const float* images_max, float* out, tcl_stream_t stream);
+size_t tcl_flow_ids_workspace_bytes(int N, int H, int W);
+int tcl_flow_ids(const float* frames, const float* flows, const float* mask_bwds, int N, int H, int W,
+                 double rgb_threshold, const float* frames_max, int* ids, long long* num_ids, void* workspace,
+                 size_t workspace_bytes, tcl_stream_t stream);
+size_t tcl_unique_inverse_workspace_bytes(long long id_range);
+int tcl_unique_inverse(const int* ids, long long n, long long id_range, long long* inverse, long long* num_unique,
+                       void* workspace, size_t workspace_bytes, tcl_stream_t stream);
 
 /* test hook: one relaxed-SSIM level (utils/loss_utils.py:73-123) forward sums and/or backward
  * of sum_p coef[p]*sum(map_p) for X, Y = [planes, h, w]; planes % 3 == 0. */

@@ -94,9 +94,62 @@ def golden_postopt(ref):
     return res
 
 
+def golden_flowid(ref):
+    """reference get_soft_mask_bwds / get_flowid / voxelization / warp_flow on the seeded scene of
+    oracle/flowid_ref.synthetic_scene (sub-pixel flows, occluder, collisions, out-of-frame targets)."""
+    from . import flowid_ref as R
+
+    out = []
+    for seed in (0, 1):
+        frames, fwd, bwd = R.synthetic_scene(n=6, h=40, w=56, seed=seed)
+        masks = ref.flow_utils.get_soft_mask_bwds(frames * 2 - 1, fwd, bwd, alpha=0.5)
+        ids = ref.flow_utils.get_flowid(frames, fwd, masks, rgb_threshold=0.05)
+        inv = ref.general_utils.voxelization(ids.view(-1, 1), frames.permute(0, 2, 3, 1).reshape(-1, 3), None, None)
+        out.append(dict(masks=masks.clone(), ids=ids.clone(), inv=inv.clone(), warp=ref.flow_utils.warp_flow(frames, bwd).clone()))
+    return out
+
+
+INV_UNET = dict(block_out_channels=(64, 128, 256, 256), cross_attention_dim=64, in_channels=4)
+
+
+def inversion_inputs():
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(6, 4, 16, 16, generator=g)
+    conds = torch.randn(1, 10, 64, generator=g).repeat(6, 1, 1)
+    return x, conds
+
+
+def golden_inversion():
+    """the reference's own Inverter.ddim_inversion / ddim_sample (invert.py:151-188) around the oracle UNet
+    (un-patched, no CFG) and the restated DDIM schedule, 5 steps, batch 4."""
+    import importlib
+    import tempfile
+
+    from .scheduler_ref import DDIMRef
+    from .unet_ref import make_unet
+
+    cwd = os.getcwd()
+    os.chdir(refshim.REF_ROOT)
+    try:
+        inv = importlib.import_module("invert")
+    finally:
+        os.chdir(cwd)
+    I = object.__new__(inv.Inverter)
+    torch.nn.Module.__init__(I)
+    I.device, I.dtype, I.unet, I.scheduler = "cpu", torch.float32, make_unet(seed=0, **INV_UNET), DDIMRef()
+    I.scheduler.set_timesteps(5)
+    I.batch_size, I.use_depth, I.control, I.save_latents = 4, False, "none", False
+    x, conds = inversion_inputs()
+    xT = I.ddim_inversion(x, conds, tempfile.mkdtemp())
+    x0 = I.ddim_sample(xT, conds)
+    return dict(x_T=xT.clone(), x_recon=x0.clone(), timesteps=I.scheduler.timesteps.clone())
+
+
 def main():
     ref = refshim.import_reference()
     os.makedirs(OUT, exist_ok=True)
+    torch.save(golden_flowid(ref), os.path.join(OUT, "flowid_producer.pt"))
+    torch.save(golden_inversion(), os.path.join(OUT, "ddim_inversion.pt"))
     torch.save(golden_vidtome(ref), os.path.join(OUT, "vidtome_compute_merge.pt"))
     torch.save(golden_sampler(ref), os.path.join(OUT, "sampler_ddim_multiaxis.pt"))
     torch.save(golden_postopt(ref), os.path.join(OUT, "postopt_stage12.pt"))

@@ -112,3 +112,30 @@ def ddim_sample_oracle(unet, x, conds, conds_t, concat_conds, n_timesteps=25, al
         if merge_global:
             reset_oracle_pool(unet)
     return x
+
+
+# ---------------------------------------------------------------------------------------------
+# DDIM inversion / reconstruction (reference invert.py:151-188, 215-244) as plain functions
+# ---------------------------------------------------------------------------------------------
+def ddim_coefs(sched, t, i, inversion: bool):
+    ts = torch.flip(sched.timesteps, [0]) if inversion else sched.timesteps
+    a_t = sched.alphas_cumprod[int(t)]
+    if inversion:
+        a_p = sched.alphas_cumprod[int(ts[i - 1])] if i > 0 else sched.final_alpha_cumprod
+    else:
+        a_p = sched.alphas_cumprod[int(ts[i + 1])] if i < len(ts) - 1 else sched.final_alpha_cumprod
+    return a_t ** 0.5, (1 - a_t) ** 0.5, a_p ** 0.5, (1 - a_p) ** 0.5
+
+
+def ddim_walk(unet, sched, x, conds, batch_size: int = 8, inversion: bool = True):
+    """x_0 -> x_T (inversion) or x_T -> x_0: eps from the un-patched UNet without CFG, batch_size frames at a time."""
+    ts = torch.flip(sched.timesteps, [0]) if inversion else sched.timesteps
+    for i, t in enumerate(ts):
+        eps = torch.cat([unet(x[b], t, encoder_hidden_states=conds[b]).sample
+                         for b in torch.arange(len(x)).split(batch_size)])
+        mu, sg, mu_p, sg_p = ddim_coefs(sched, t, i, inversion)
+        if inversion:
+            x = mu * ((x - sg_p * eps) / mu_p) + sg * eps
+        else:
+            x = mu_p * ((x - sg * eps) / mu) + sg_p * eps
+    return x

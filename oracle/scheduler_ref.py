@@ -121,3 +121,19 @@ class DPMSolverSDEKarras:
 
     def scale_model_input(self, sample, *a, **k):
         return sample
+
+
+class DDIMRef:
+    """diffusers 0.32.1 DDIMScheduler, the attributes Inverter reads (reference invert.py:56-59, 219-233), for the
+    SD-1.5 scheduler config (scaled_linear 0.00085..0.012, leading spacing, steps_offset 1, set_alpha_to_one
+    False).  Restated from the published algorithm; parity unpinned (diffusers is not installable here)."""
+
+    def __init__(self):
+        betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.final_alpha_cumprod = self.alphas_cumprod[0]
+        self.timesteps = torch.arange(999, -1, -1)
+
+    def set_timesteps(self, n, device=None):
+        ratio = 1000 // n
+        self.timesteps = torch.from_numpy((np.arange(0, n) * ratio).round()[::-1].copy().astype(np.int64) + 1)

@@ -244,3 +244,27 @@ lib.tcl_exposure_gradient.restype = C.c_int
 lib.tcl_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float,
                               C.c_float, C.c_int, C.c_void_p]
 lib.tcl_adam_step.restype = C.c_int
+
+lib.tcl_debug_attention_variant.argtypes = [C.c_int]
+lib.tcl_debug_attention_variant.restype = C.c_int
+lib.tcl_ddim_next.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float,
+                              C.c_float, C.c_void_p]
+lib.tcl_ddim_next.restype = C.c_int
+
+lib.tcl_warp_bicubic.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+lib.tcl_warp_bicubic.restype = C.c_int
+lib.tcl_max_f32.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
+lib.tcl_max_f32.restype = C.c_int
+lib.tcl_soft_mask_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                  C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.tcl_soft_mask_bwd.restype = C.c_int
+lib.tcl_flow_ids_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+lib.tcl_flow_ids_workspace_bytes.restype = C.c_size_t
+lib.tcl_flow_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+lib.tcl_flow_ids.restype = C.c_int
+lib.tcl_unique_inverse_workspace_bytes.argtypes = [C.c_longlong]
+lib.tcl_unique_inverse_workspace_bytes.restype = C.c_size_t
+lib.tcl_unique_inverse.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                   C.c_void_p]
+lib.tcl_unique_inverse.restype = C.c_int

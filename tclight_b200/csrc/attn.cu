@@ -68,7 +68,24 @@ __device__ __forceinline__ float poly_exp2(float x) {
   return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
 }
 
-template <int NQ, int DPAD, int KST, int VST, bool BF16>
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (P, 16-bit pairs packed in 32-bit TMEM columns, one row per
+// lane) is read straight from tensor memory, so P never crosses shared memory.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// TS   : P is handed to the P V MMA through TMEM (tcgen05.st + A-from-TMEM MMA) instead of swizzled smem.
+// POLY : of every 8 exponentials, how many run as FMA-pipe polynomials (poly_exp2) instead of MUFU.EX2.
+// STAG : softmax warpgroup q starts q*STAG clocks late, so the warpgroups' MUFU phases interleave.
+template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS, int POLY, int STAG>
 __global__ void __launch_bounds__(NQ * 128 + 64, 1)
 attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnParams p) {
   using E = Elem<BF16>;
@@ -81,8 +98,10 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
   constexpr uint32_t OFF_K = OFF_Q + NQ * QK_TILE;
   constexpr uint32_t OFF_V = OFF_K + KST * QK_TILE;
   constexpr uint32_t OFF_P = OFF_V + VST * V_TILE;
-  constexpr uint32_t OFF_BAR = OFF_P + NQ * P_TILE;
-  constexpr uint32_t TMEM_NEED = NQ * (128 + DPAD);
+  constexpr uint32_t OFF_BAR = OFF_P + (TS ? 0 : NQ * P_TILE);
+  constexpr uint32_t TMEM_P = NQ * (128 + DPAD);      // TS: 64 columns of packed P per Q tile
+  constexpr uint32_t TMEM_NEED = NQ * (128 + DPAD + (TS ? 64 : 0));
+  static_assert(TMEM_NEED <= 512, "TMEM budget");
   constexpr uint32_t TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
   constexpr int SOFT_THREADS = NQ * 128;
 
@@ -221,11 +240,18 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
           tcgen05_fence_after();
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            const uint64_t a = umma_desc_k_sw128(p_base + q * P_TILE + c * 16384);
             const uint64_t bd = umma_desc_k_sw128(v_base + st * V_TILE + c * V_CHUNK);
+            if (TS) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_ss(tmem_base + NQ * 128 + q * DPAD, a + 2 * k, bd + 2 * k, idesc_o, (j | c | k) != 0);
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ts(tmem_base + NQ * 128 + q * DPAD, tmem_base + TMEM_P + q * 64 + (c * 4 + k) * 8, bd + 2 * k,
+                            idesc_o, (j | c | k) != 0);
+            } else {
+              const uint64_t a = umma_desc_k_sw128(p_base + q * P_TILE + c * 16384);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ss(tmem_base + NQ * 128 + q * DPAD, a + 2 * k, bd + 2 * k, idesc_o, (j | c | k) != 0);
+            }
           }
           umma_commit(&p_empty[q]);
           ++pn[q];
@@ -243,7 +269,12 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
     const uint32_t t_s = t_lane + q * 128;
     const uint32_t t_o = t_lane + NQ * 128 + q * DPAD;
     float m_ref = -INFINITY;                 // reference max (scaled, log2 domain) used by exp2
-    const uint32_t p_tile_addr = smem_u32(smem + OFF_P + q * P_TILE);
+    const uint32_t p_tile_addr = smem_u32(smem + OFF_P + (TS ? 0 : q * P_TILE));
+    const uint32_t t_p = t_lane + TMEM_P + q * 64;
+    if (STAG > 0 && q > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)STAG * q) {}
+    }
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[q], j & 1);
       tcgen05_fence_after();
@@ -294,8 +325,8 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
         for (int i = 0; i < 32; i += 2) {
           const float a0 = fmaf(__uint_as_float(s[i]), p.scale_log2, -m_ref);
           const float a1 = fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_ref);
-          const float e0 = ((i & 7) < TCL_ATTN_POLY) ? poly_exp2<BF16>(a0) : fast_exp2(a0);
-          const float e1 = (((i + 1) & 7) < TCL_ATTN_POLY) ? poly_exp2<BF16>(a1) : fast_exp2(a1);
+          const float e0 = ((i & 7) < POLY) ? poly_exp2<BF16>(a0) : fast_exp2(a0);
+          const float e1 = (((i + 1) & 7) < POLY) ? poly_exp2<BF16>(a1) : fast_exp2(a1);
           pk[(c0 + i) >> 1] = E::pack(e0, e1);
         }
       };
@@ -316,19 +347,28 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
         }
         tmem_st_wait();
       }
+      if (TS) {
+        // P -> TMEM: lane = row, 32-bit column c holds keys (2c, 2c+1) — the K-major A operand of the P V MMA
+        uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[0]);
+        uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
+        tmem_st_32x32b_x32(t_p, lo);
+        tmem_st_32x32b_x32(t_p + 32, hi);
+        tmem_st_wait();
+      } else {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint32_t rowa = p_tile_addr + c * 16384 + row * 128;
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t rowa = p_tile_addr + c * 16384 + row * 128;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int pu = u ^ (row & 7);
-          // explicit st.shared.v4: a generic-pointer store compiles to ST.E + splits into 32/64-bit pieces
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + pu * 16), "r"(pk[c * 32 + u * 4 + 0]),
-                       "r"(pk[c * 32 + u * 4 + 1]), "r"(pk[c * 32 + u * 4 + 2]), "r"(pk[c * 32 + u * 4 + 3])
-                       : "memory");
+          for (int u = 0; u < 8; ++u) {
+            const int pu = u ^ (row & 7);
+            // explicit st.shared.v4: a generic-pointer store compiles to ST.E + splits into 32/64-bit pieces
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + pu * 16), "r"(pk[c * 32 + u * 4 + 0]),
+                         "r"(pk[c * 32 + u * 4 + 1]), "r"(pk[c * 32 + u * 4 + 2]), "r"(pk[c * 32 + u * 4 + 3])
+                         : "memory");
+          }
         }
+        fence_proxy_async_smem();
       }
-      fence_proxy_async_smem();
       tcgen05_fence_before();
       mbar_arrive(&p_full[q]);
     }
@@ -373,13 +413,13 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
   }
 }
 
-template <int NQ, int DPAD, int KST, int VST, bool BF16>
+template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS = false, int POLY = 0, int STAG = 0>
 static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, int bh, cudaStream_t stream) {
   constexpr size_t smem = (size_t)NQ * 128 * DPAD * 2 + (size_t)KST * 128 * DPAD * 2 +
-                          (size_t)VST * 2 * DPAD * 128 + (size_t)NQ * 128 * 128 * 2 + 1024 + 256;
+                          (size_t)VST * 2 * DPAD * 128 + (TS ? 0 : (size_t)NQ * 128 * 128 * 2) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NQ, DPAD, KST, VST, BF16>,
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_last_error("attention: cudaFuncSetAttribute(%zu B) failed: %s", smem, cudaGetErrorString(e));
@@ -388,7 +428,7 @@ static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, in
     configured = true;
   }
   dim3 grid((q_tiles + NQ - 1) / NQ, bh);
-  attn_kernel<NQ, DPAD, KST, VST, BF16><<<grid, NQ * 128 + 64, smem, stream>>>(tm, p);
+  attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG><<<grid, NQ * 128 + 64, smem, stream>>>(tm, p);
   TCL_CHECK_LAUNCH("tcl_attention");
   return TCL_OK;
 }
@@ -396,6 +436,8 @@ static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, in
 }  // namespace tcl
 
 using namespace tcl;
+
+static int g_attn_variant = 0;
 
 extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
   TCL_CHECK_ARG(a != nullptr, "tcl_attention: null descriptor");
@@ -439,14 +481,41 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
   p.out = a->out;
   p.out_pitch = (long long)a->heads * a->d;
   const int q_tiles = (a->tq + 127) / 128;
+  const int var = g_attn_variant;
   if (a->d_pad == 64) {
-    return bf16 ? launch_attn<2, 64, 3, 2, true>(tm, p, q_tiles, bh, stream)
-                : launch_attn<2, 64, 3, 2, false>(tm, p, q_tiles, bh, stream);
+    if (!bf16) {
+      return var >= 1 ? launch_attn<2, 64, 4, 3, false, true>(tm, p, q_tiles, bh, stream)
+                      : launch_attn<2, 64, 3, 2, false>(tm, p, q_tiles, bh, stream);
+    }
+    switch (var) {
+      case 1: return launch_attn<2, 64, 4, 3, true, true, 0, 0>(tm, p, q_tiles, bh, stream);
+      case 2: return launch_attn<2, 64, 4, 3, true, true, 0, 1200>(tm, p, q_tiles, bh, stream);
+      case 3: return launch_attn<2, 64, 4, 3, true, true, 2, 0>(tm, p, q_tiles, bh, stream);
+      case 4: return launch_attn<2, 64, 4, 3, true, true, 3, 1200>(tm, p, q_tiles, bh, stream);
+      case 5: return launch_attn<2, 64, 3, 2, true, false, 0, 1200>(tm, p, q_tiles, bh, stream);
+      case 6: return launch_attn<2, 64, 4, 3, true, true, 2, 1200>(tm, p, q_tiles, bh, stream);
+      case 7: return launch_attn<2, 64, 4, 3, true, true, 0, 2000>(tm, p, q_tiles, bh, stream);
+      default: return launch_attn<2, 64, 3, 2, true>(tm, p, q_tiles, bh, stream);
+    }
   } else if (a->d_pad == 128) {
+    if (var >= 1)
+      return bf16 ? launch_attn<1, 128, 3, 2, true, true>(tm, p, q_tiles, bh, stream)
+                  : launch_attn<1, 128, 3, 2, false, true>(tm, p, q_tiles, bh, stream);
     return bf16 ? launch_attn<1, 128, 2, 2, true>(tm, p, q_tiles, bh, stream)
                 : launch_attn<1, 128, 2, 2, false>(tm, p, q_tiles, bh, stream);
   } else {
+    if (var >= 1)
+      return bf16 ? launch_attn<1, 192, 2, 2, true, true>(tm, p, q_tiles, bh, stream)
+                  : launch_attn<1, 192, 2, 2, false, true>(tm, p, q_tiles, bh, stream);
     return bf16 ? launch_attn<1, 192, 2, 1, true>(tm, p, q_tiles, bh, stream)
                 : launch_attn<1, 192, 2, 1, false>(tm, p, q_tiles, bh, stream);
   }
+}
+
+// Tuning hook: selects the kernel variant used by tcl_attention (0 = P through shared memory; 1.. = P through
+// TMEM with different exp2 / stagger settings, see the dispatch above).  Returns the previous value.
+extern "C" int tcl_debug_attention_variant(int v) {
+  const int old = g_attn_variant;
+  g_attn_variant = v;
+  return old;
 }

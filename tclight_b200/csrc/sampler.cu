@@ -109,6 +109,19 @@ __global__ void dpm_step_kernel(const T* __restrict__ eps, const T* __restrict__
   }
 }
 
+// DDIM step in either direction (invert.py:215-244 pred_next_x): x' = mu_out*((x - sig_in*eps)/mu_in) + sig_out*eps,
+// every tensor op rounded to the latent dtype like the reference's fp16 expression
+template <typename T>
+__global__ void ddim_next_kernel(const T* __restrict__ eps, const T* __restrict__ x, T* __restrict__ x_out, long long n,
+                                 float mu_in, float sig_in, float mu_out, float sig_out) {
+  using Lt = Lat<T>;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float e = Lt::ld(eps + i), xs = Lt::ld(x + i);
+    const float x0 = Lt::R(Lt::R(xs - Lt::R(sig_in * e)) / mu_in);
+    Lt::st(x_out + i, Lt::R(mu_out * x0) + Lt::R(sig_out * e));
+  }
+}
+
 static inline int grid_n(long long total, int block) {
   long long g = (total + block - 1) / block;
   if (g > 148 * 8) g = 148 * 8;
@@ -156,5 +169,18 @@ extern "C" int tcl_dpm_step(int latent_dtype, const void* eps, const void* x, co
   else if (latent_dtype == TCL_LATENT_BF16) dpm_step_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)eps, (const __nv_bfloat16*)x, (const __nv_bfloat16*)x0_prev, z, (__nv_bfloat16*)x0_out, (__nv_bfloat16*)x_out, n, c);
   else { set_last_error("tcl_dpm_step: latent dtype %d", latent_dtype); return TCL_ERR_ARG; }
   TCL_CHECK_LAUNCH("tcl_dpm_step");
+  return TCL_OK;
+}
+
+extern "C" int tcl_ddim_next(int latent_dtype, const void* eps, const void* x, void* x_out, long long n, float mu_in,
+                             float sig_in, float mu_out, float sig_out, cudaStream_t stream) {
+  TCL_CHECK_ARG(eps && x && x_out && n > 0, "tcl_ddim_next: args");
+  TCL_CHECK_ARG(mu_in != 0.f, "tcl_ddim_next: mu_in == 0");
+  const int g = grid_n(n, 256);
+  if (latent_dtype == TCL_LATENT_FP32) ddim_next_kernel<float><<<g, 256, 0, stream>>>((const float*)eps, (const float*)x, (float*)x_out, n, mu_in, sig_in, mu_out, sig_out);
+  else if (latent_dtype == TCL_LATENT_FP16) ddim_next_kernel<__half><<<g, 256, 0, stream>>>((const __half*)eps, (const __half*)x, (__half*)x_out, n, mu_in, sig_in, mu_out, sig_out);
+  else if (latent_dtype == TCL_LATENT_BF16) ddim_next_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)eps, (const __nv_bfloat16*)x, (__nv_bfloat16*)x_out, n, mu_in, sig_in, mu_out, sig_out);
+  else { set_last_error("tcl_ddim_next: latent dtype %d", latent_dtype); return TCL_ERR_ARG; }
+  TCL_CHECK_LAUNCH("tcl_ddim_next");
   return TCL_OK;
 }

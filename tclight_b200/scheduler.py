@@ -118,3 +118,42 @@ class DPMSolverMultistepSchedulerB200:
 
     def scale_model_input(self, sample, *a, **k):
         return sample
+
+
+class DDIMSchedulerB200:
+    """The part of diffusers' ``DDIMScheduler`` the reference's ``Inverter`` reads (invert.py:56-59, 151-244):
+    ``set_timesteps`` / ``timesteps`` / ``alphas_cumprod`` / ``final_alpha_cumprod``, for the SD-1.5 scheduler
+    config loaded at utils/VidToMe/utils.py:40-41 (scaled-linear betas 0.00085..0.012, 1000 train steps,
+    ``timestep_spacing="leading"``, ``steps_offset=1``, ``set_alpha_to_one=False``).  The update itself is
+    the Inverter's closed form (tcl_ddim_next), not ``scheduler.step``."""
+
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                 set_alpha_to_one=False, steps_offset=1, timestep_spacing="leading"):
+        if beta_schedule == "scaled_linear":
+            betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        elif beta_schedule == "linear":
+            betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        else:
+            raise NotImplementedError(beta_schedule)
+        if timestep_spacing != "leading":
+            raise NotImplementedError("only the 'leading' spacing of the SD-1.5 scheduler config is implemented")
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.num_train_timesteps = num_train_timesteps
+        self.steps_offset = steps_offset
+        self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
+
+    def set_timesteps(self, num_inference_steps, device=None):
+        if num_inference_steps > self.num_train_timesteps:
+            raise ValueError("num_inference_steps exceeds num_train_timesteps")
+        self.num_inference_steps = num_inference_steps
+        step_ratio = self.num_train_timesteps // num_inference_steps
+        ts = (np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(np.int64)
+        ts += self.steps_offset
+        self.timesteps = torch.from_numpy(ts).to(device)
+
+    def scale_model_input(self, sample, *a, **k):
+        return sample

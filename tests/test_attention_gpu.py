@@ -42,3 +42,31 @@ def test_attention(cuda, dtype, B, H, Tq, Tk, d, div):
     ref = torch.einsum("bhqk,bhkd->bhqd", s.softmax(-1), vv).permute(0, 2, 1, 3).reshape(B, Tq, H * d)
     err = ((out.float() - ref).norm() / ref.norm()).item()
     assert err < TOL[dtype], err
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_attention_variants(cuda, dtype, variant):
+    """Every tuning variant of the kernel (P through TMEM, FMA-pipe exp2 share, warpgroup stagger) is held to the
+    same tolerance as the default one."""
+    from tclight_b200 import ops
+    from tclight_b200._lib import lib
+
+    old = lib.tcl_debug_attention_variant(variant)
+    try:
+        for (B, H, Tq, Tk, d, div) in [(2, 8, 1024, 1024, 40, 1), (2, 8, 300, 300, 40, 1), (1, 8, 257, 640, 80, 1),
+                                       (2, 8, 130, 130, 160, 1), (4, 8, 200, 154, 40, 2)]:
+            torch.manual_seed(0)
+            d_pad = ops.head_pad(d)
+            q, qp = _mk(B, H, Tq, d, d_pad, dtype, cuda, 1.5)
+            k, kp = _mk(B // div, H, Tk, d, d_pad, dtype, cuda, 1.5)
+            v, vp = _mk(B // div, H, Tk, d, d_pad, dtype, cuda)
+            out = ops.attention(qp, kp, vp.transpose(2, 3).contiguous(), Tq, Tk, d, kv_batch_div=div)
+            kk = k.float().repeat_interleave(div, dim=0)
+            vv = v.float().repeat_interleave(div, dim=0)
+            s = torch.einsum("bhqd,bhkd->bhqk", q.float(), kk) / d ** 0.5
+            ref = torch.einsum("bhqk,bhkd->bhqd", s.softmax(-1), vv).permute(0, 2, 1, 3).reshape(B, Tq, H * d)
+            err = ((out.float() - ref).norm() / ref.norm()).item()
+            assert err < TOL[dtype], (variant, d, err)
+    finally:
+        lib.tcl_debug_attention_variant(old)

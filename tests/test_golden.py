@@ -67,3 +67,44 @@ def test_postopt_golden():
         assert torch.allclose(got_l, want["losses"], rtol=0, atol=1e-6, equal_nan=True)
         assert torch.allclose(img.double().mean(dim=(2, 3)), want["image_mean"], atol=1e-6)
         assert torch.allclose(img[:, :, ::37, ::41], want["image_probe"], atol=1e-5)
+
+
+def test_flowid_producer_golden():
+    """soft masks / flow ids / unique inverse / bicubic warp restatements vs the reference's own outputs."""
+    from oracle import flowid_ref as R
+
+    gold = torch.load(os.path.join(GOLD, "flowid_producer.pt"))
+    for seed, want in enumerate(gold):
+        frames, fwd, bwd = R.synthetic_scene(n=6, h=40, w=56, seed=seed)
+        masks = R.soft_mask_bwds(frames * 2 - 1, fwd, bwd, alpha=0.5)
+        assert torch.allclose(masks, want["masks"], rtol=0, atol=2e-6)
+        ids = R.flow_ids(frames, fwd, want["masks"], rgb_threshold=0.05)
+        assert ids.dtype == torch.int32 and torch.equal(ids, want["ids"])
+        assert torch.equal(R.unique_inverse(ids), want["inv"].reshape(-1))
+        assert torch.allclose(R.warp(frames, bwd), want["warp"], rtol=0, atol=1e-6)
+        # the scene exercises what it claims to
+        assert 0.2 < (want["masks"] > 0.5).float().mean() < 0.95
+        assert int(want["ids"].max()) + 1 < want["ids"].numel()
+
+
+def test_ddim_inversion_golden():
+    from oracle import make_goldens as G, pipeline_ref as P
+    from oracle.scheduler_ref import DDIMRef
+    from oracle.unet_ref import make_unet
+    from tclight_b200.scheduler import DDIMSchedulerB200
+
+    gold = torch.load(os.path.join(GOLD, "ddim_inversion.pt"))
+    x, conds = G.inversion_inputs()
+    sch = DDIMRef()
+    sch.set_timesteps(5)
+    assert torch.equal(sch.timesteps, gold["timesteps"])
+    prod = DDIMSchedulerB200()
+    prod.set_timesteps(5)
+    assert torch.equal(prod.timesteps, gold["timesteps"]) and torch.equal(prod.alphas_cumprod, sch.alphas_cumprod)
+    assert torch.equal(prod.final_alpha_cumprod, sch.final_alpha_cumprod)
+    unet = make_unet(seed=0, **G.INV_UNET)
+    with torch.no_grad():
+        xT = P.ddim_walk(unet, sch, x, conds, 4, True)
+        x0 = P.ddim_walk(unet, sch, xT, conds, 4, False)
+    assert torch.allclose(xT, gold["x_T"], rtol=1e-4, atol=1e-4)
+    assert torch.allclose(x0, gold["x_recon"], rtol=1e-4, atol=1e-4)

@@ -130,3 +130,41 @@ def test_stage1_oracle_matches_reference(ref, monkeypatch):
     assert len(got_loss) == len(want_loss)
     assert max(abs(a - b) for a, b in zip(got_loss, want_loss)) < 1e-6
     assert (got_img - want_img).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("seed,alpha,thr", [(0, 0.5, 0.05), (1, 0.1, 0.01), (2, 0.5, 0.2)])
+def test_flowid_producer_matches_reference(ref, seed, alpha, thr):
+    """get_soft_mask_bwds / get_flowid / voxelization / warp_flow (utils/flow_utils.py, general_utils.py:223) vs
+    oracle/flowid_ref.py, including the last-writer-wins collision rule of the CPU index assignment."""
+    from oracle import flowid_ref as R
+
+    frames, fwd, bwd = R.synthetic_scene(n=5, h=36, w=44, seed=seed)
+    m_ref = ref.flow_utils.get_soft_mask_bwds(frames * 2 - 1, fwd, bwd, alpha=alpha)
+    m = R.soft_mask_bwds(frames * 2 - 1, fwd, bwd, alpha=alpha)
+    assert torch.allclose(m, m_ref, rtol=0, atol=1e-6)
+    ids_ref = ref.flow_utils.get_flowid(frames, fwd, m_ref, rgb_threshold=thr)
+    ids = R.flow_ids(frames, fwd, m_ref, rgb_threshold=thr)
+    assert torch.equal(ids, ids_ref)
+    inv_ref = ref.general_utils.voxelization(ids_ref.view(-1, 1), frames.permute(0, 2, 3, 1).reshape(-1, 3), None, None)
+    assert torch.equal(R.unique_inverse(ids), inv_ref.reshape(-1))
+    # non-dense ids: the inverse is a true rank map, not the identity
+    sparse = ids_ref.reshape(-1) * 3 + 7
+    inv2 = ref.general_utils.voxelization(sparse.view(-1, 1), torch.zeros(sparse.numel(), 3), None, None)
+    assert torch.equal(R.unique_inverse(sparse), inv2.reshape(-1))
+    assert torch.equal(R.warp(frames, bwd), ref.flow_utils.warp_flow(frames, bwd))
+
+
+def test_ddim_inversion_matches_reference_inverter(ref):
+    from oracle import make_goldens as G, pipeline_ref as P
+    from oracle.scheduler_ref import DDIMRef
+    from oracle.unet_ref import make_unet
+
+    gold = G.golden_inversion()
+    x, conds = G.inversion_inputs()
+    sch = DDIMRef()
+    sch.set_timesteps(5)
+    unet = make_unet(seed=0, **G.INV_UNET)
+    with torch.no_grad():
+        xT = P.ddim_walk(unet, sch, x, conds, 4, True)
+        assert torch.equal(xT, gold["x_T"])
+        assert torch.equal(P.ddim_walk(unet, sch, xT, conds, 4, False), gold["x_recon"])
