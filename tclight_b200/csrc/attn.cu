@@ -14,8 +14,8 @@
 // accumulates O += P V in TMEM.  The softmax denominator rides along as one extra output column:
 // row `d` of every V^T tile is overwritten with ones in shared memory, so O[:, d] = sum_j P_ij
 // (from the same rounded P as the numerator) and is rescaled together with O.
-// Warp roles: NQ softmax warpgroups (one 128-row Q tile each, ping-pong against the single MMA
-// issuer), one TMA warp, one MMA warp.
+// Warp roles: NQ softmax warpgroups (one 128-row Q tile each), one TMA warp, NQ MMA-issuer warps (one per Q
+// tile, running converged with one elected lane issuing).
 #include "common.cuh"
 #include "tmap.h"
 #include "tclight.h"
@@ -34,7 +34,18 @@ struct AttnParams {
   float scale_log2;    // log2(e) / sqrt(d)
   void* out;           // [B, tq, heads*d]
   long long out_pitch; // heads*d
+  long long* trace;    // TCL_ATTN_TRACE builds only: clock64 event log of CTA (0,0)
 };
+
+#ifdef TCL_ATTN_TRACE
+#define TRACE_EV(role, ev, j)                                                                          \
+  do {                                                                                                 \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (j) >= 64 && (j) < 72)                        \
+      p.trace[(((role) * 8 + ((j) - 64)) * 8 + (ev))] = clock64();                                     \
+  } while (0)
+#else
+#define TRACE_EV(role, ev, j) do {} while (0)
+#endif
 
 struct AttnTmaps {
   CUtensorMap q, k, vt;
@@ -86,7 +97,7 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 // POLY : of every 8 exponentials, how many run as FMA-pipe polynomials (poly_exp2) instead of MUFU.EX2.
 // STAG : softmax warpgroup q starts q*STAG clocks late, so the warpgroups' MUFU phases interleave.
 template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS, int POLY, int STAG>
-__global__ void __launch_bounds__(NQ * 128 + 64, 1)
+__global__ void __launch_bounds__(NQ * 128 + 32 + NQ * 32, 1)
 attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnParams p) {
   using E = Elem<BF16>;
   constexpr int NC = DPAD / 64;                    // 64-wide chunks of the head dim
@@ -118,8 +129,8 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
   uint64_t* s_empty = s_full + NQ;          // NQ
   uint64_t* p_full = s_empty + NQ;          // NQ
   uint64_t* p_empty = p_full + NQ;          // NQ
-  uint64_t* o_full = p_empty + NQ;          // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* o_full = p_empty + NQ;          // NQ
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + NQ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -134,22 +145,23 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
     tma_prefetch_desc(&tm.k);
     tma_prefetch_desc(&tm.vt);
     mbar_init(q_full, 1);
-    for (int i = 0; i < KST; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-    for (int i = 0; i < VST; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < KST; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], NQ); }
+    for (int i = 0; i < VST; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], NQ); }
     for (int i = 0; i < NQ; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 128);
       mbar_init(&p_full[i], 128);
       mbar_init(&p_empty[i], 1);
+      mbar_init(&o_full[i], 1);
     }
-    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == SOFT_THREADS / 32 + 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // warp-uniform for the compiler (a plain shared-memory load is treated as divergent)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == SOFT_THREADS / 32) {
     // ===================== TMA producer =====================
@@ -178,88 +190,83 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
         }
       }
     }
-  } else if (warp == SOFT_THREADS / 32 + 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(BF16, 128, 128);
-      constexpr uint32_t idesc_o = umma_idesc_f16(BF16, 128, DPAD);
-      int kn = 0, vn = 0;
-      int sn[NQ], pn[NQ];
-      for (int q = 0; q < NQ; ++q) { sn[q] = 0; pn[q] = 0; }
-      const uint32_t q_base = smem_u32(smem + OFF_Q);
-      const uint32_t k_base = smem_u32(smem + OFF_K);
-      const uint32_t v_base = smem_u32(smem + OFF_V);
-      const uint32_t p_base = smem_u32(smem + OFF_P);
+  } else if (warp > SOFT_THREADS / 32) {
+    // ===================== MMA issuers: one converged warp per Q tile =====================
+    // All 32 lanes run the control flow (so every operand stays in uniform registers and no per-MMA
+    // ELECT/R2UR.BROADCAST waterfall is generated — with a single `if (lane == 0)` issuer that waterfall plus
+    // ~150-clk barrier probes made this thread, not the softmax, the critical path: 3 800 clk per KV tile);
+    // one elected lane issues the tcgen05 instructions.
+    const int q = warp - (SOFT_THREADS / 32 + 1);
+    constexpr uint32_t idesc_s = umma_idesc_f16(BF16, 128, 128);
+    constexpr uint32_t idesc_o = umma_idesc_f16(BF16, 128, DPAD);
+    const uint32_t q_base = smem_u32(smem + OFF_Q) + q * QK_TILE;
+    const uint32_t k_base = smem_u32(smem + OFF_K);
+    const uint32_t v_base = smem_u32(smem + OFF_V);
+    const uint32_t p_base = smem_u32(smem + OFF_P) + (TS ? 0 : q * P_TILE);
+    const uint32_t t_s = tmem_base + q * 128;
+    const uint32_t t_o = tmem_base + NQ * 128 + q * DPAD;
+    const uint32_t t_p = tmem_base + TMEM_P + q * 64;
 
-      auto issue_qk_all = [&]() {
-        const int st = kn % KST;
-        mbar_wait(&k_full[st], (kn / KST) & 1);
-        tcgen05_fence_after();
-        for (int q = 0; q < NQ; ++q) {
-          mbar_wait(&s_empty[q], (sn[q] & 1) ^ 1);
-          tcgen05_fence_after();
-#pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            const uint64_t a = umma_desc_k_sw128(q_base + q * QK_TILE + c * 16384);
-            const uint64_t bd = umma_desc_k_sw128(k_base + st * QK_TILE + c * 16384);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_ss(tmem_base + q * 128, a + 2 * k, bd + 2 * k, idesc_s, (c | k) != 0);
-          }
-          umma_commit(&s_full[q]);
-          ++sn[q];
-        }
-        umma_commit(&k_empty[st]);
-        ++kn;
-      };
-
-      mbar_wait(q_full, 0);
+    auto issue_qk = [&](int jn) {
+      const int st = jn % KST;
+      mbar_wait(&k_full[st], (jn / KST) & 1);
+      TRACE_EV(2, q * 4 + 0, jn);
+      mbar_wait(&s_empty[q], (jn & 1) ^ 1);
+      TRACE_EV(2, q * 4 + 1, jn);
       tcgen05_fence_after();
-      // scores run one tile ahead of P V
-      issue_qk_all();
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) issue_qk_all();
-        const int st = vn % VST;
-        mbar_wait(&v_full[st], (vn / VST) & 1);
-        {
-          // row `d` of V^T := 1  => O[:, d] accumulates the softmax denominator (swizzle only
-          // permutes 16-byte units inside a 128-byte row, so filling the whole row is layout-safe)
-          const uint32_t one2 = BF16 ? 0x3F803F80u : 0x3C003C00u;
+      if (elect_one()) {
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const uint32_t rowa = v_base + st * V_TILE + c * V_CHUNK + p.d * 128;
+        for (int c = 0; c < NC; ++c) {
+          const uint64_t a = umma_desc_k_sw128(q_base + c * 16384);
+          const uint64_t bd = umma_desc_k_sw128(k_base + st * QK_TILE + c * 16384);
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(rowa + u * 16), "r"(one2) : "memory");
-          }
-          fence_proxy_async_smem();
+          for (int k = 0; k < 4; ++k) umma_f16_ss(t_s, a + 2 * k, bd + 2 * k, idesc_s, (c | k) != 0);
         }
-        tcgen05_fence_after();
-        for (int q = 0; q < NQ; ++q) {
-          mbar_wait(&p_full[q], pn[q] & 1);
-          tcgen05_fence_after();
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const uint64_t bd = umma_desc_k_sw128(v_base + st * V_TILE + c * V_CHUNK);
-            if (TS) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16_ts(tmem_base + NQ * 128 + q * DPAD, tmem_base + TMEM_P + q * 64 + (c * 4 + k) * 8, bd + 2 * k,
-                            idesc_o, (j | c | k) != 0);
-            } else {
-              const uint64_t a = umma_desc_k_sw128(p_base + q * P_TILE + c * 16384);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16_ss(tmem_base + NQ * 128 + q * DPAD, a + 2 * k, bd + 2 * k, idesc_o, (j | c | k) != 0);
-            }
-          }
-          umma_commit(&p_empty[q]);
-          ++pn[q];
-        }
-        umma_commit(&v_empty[st]);
-        ++vn;
+        umma_commit(&s_full[q]);
+        umma_commit(&k_empty[st]);       // k_empty counts NQ commits
       }
-      umma_commit(o_full);
+      __syncwarp();
+    };
+
+    mbar_wait(q_full, 0);
+    tcgen05_fence_after();
+    issue_qk(0);                          // scores run one tile ahead of P V
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) issue_qk(j + 1);
+      const int st = j % VST;
+      mbar_wait(&v_full[st], (j / VST) & 1);
+      // row `d` of V^T := 1  => O[:, d] accumulates the softmax denominator (swizzle only permutes 16-byte units
+      // inside a 128-byte row, so filling the whole row is layout-safe).  Every issuer warp writes the same
+      // values; 16 lanes store one 16-byte unit each.
+      if (lane < 16) {
+        const uint32_t one2 = BF16 ? 0x3F803F80u : 0x3C003C00u;
+        const uint32_t rowa = v_base + st * V_TILE + (lane >> 3) * V_CHUNK + p.d * 128 + (lane & 7) * 16;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(rowa), "r"(one2) : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      TRACE_EV(2, q * 4 + 2, j);
+      mbar_wait(&p_full[q], j & 1);
+      TRACE_EV(2, q * 4 + 3, j);
+      tcgen05_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint64_t bd = umma_desc_k_sw128(v_base + st * V_TILE + c * V_CHUNK);
+          if (TS) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ts(t_o, t_p + (c * 4 + k) * 8, bd + 2 * k, idesc_o, (j | c | k) != 0);
+          } else {
+            const uint64_t a = umma_desc_k_sw128(p_base + c * 16384);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ss(t_o, a + 2 * k, bd + 2 * k, idesc_o, (j | c | k) != 0);
+          }
+        }
+        umma_commit(&p_empty[q]);
+        umma_commit(&v_empty[st]);       // v_empty counts NQ commits
+        if (j + 1 == n_kv) umma_commit(&o_full[q]);
+      }
+      __syncwarp();
     }
   } else {
     // ===================== softmax warpgroups =====================
@@ -275,20 +282,25 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       const long long t0 = clock64();
       while (clock64() - t0 < (long long)STAG * q) {}
     }
+    // A barrier probe costs ~250 clk even when the phase is long complete (measured with the clock64 trace), so
+    // both per-tile barriers are probed early with the non-blocking form and the result is consumed later: the
+    // blocking wait only runs when the early probe failed.
+    bool s_ready = false;
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[q], j & 1);
+      if (threadIdx.x == q * 128) TRACE_EV(q, 0, j);
+      if (!s_ready) mbar_wait(&s_full[q], j & 1);
+      if (threadIdx.x == q * 128) TRACE_EV(q, 1, j);
       tcgen05_fence_after();
       uint32_t s0[32], s1[32], s2[32], s3[32];
       tmem_ld_32x32b_x32(t_s + 0, s0);
       tmem_ld_32x32b_x32(t_s + 32, s1);
       tmem_ld_32x32b_x32(t_s + 64, s2);
       tmem_ld_32x32b_x32(t_s + 96, s3);
-      // the previous P V MMA must be done before P (smem) or O (TMEM) are touched; checking here hides the
-      // barrier round trip behind the TMEM load
-      mbar_wait(&p_empty[q], (j & 1) ^ 1);
+      const bool pe_ready = mbar_test_wait(&p_empty[q], (j & 1) ^ 1);   // P V of the previous tile: consumed after the exps
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(&s_empty[q]);
+      if (threadIdx.x == q * 128) TRACE_EV(q, 2, j);
       const int valid_cols = p.tk - j * 128;
       const bool tail = valid_cols < 128;      // warp-uniform: only the last KV tile
       if (tail) {
@@ -334,6 +346,13 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       do_chunk(s1, 32);
       do_chunk(s2, 64);
       do_chunk(s3, 96);
+      // the previous P V MMA must be done before P or O are touched.  Waiting here (not before the exponentials)
+      // gives it the whole softmax of this tile to complete: the ncu source view of the earlier placement showed
+      // a third of all stall samples on this barrier.
+      if (threadIdx.x == q * 128) TRACE_EV(q, 3, j);
+      s_ready = (j + 1 < n_kv) && mbar_test_wait(&s_full[q], (j + 1) & 1);   // next scores: consumed at the loop top
+      if (!pe_ready) mbar_wait(&p_empty[q], (j & 1) ^ 1);
+      if (threadIdx.x == q * 128) TRACE_EV(q, 4, j);
       if (__any_sync(0xffffffffu, factor != 1.f)) {
         tcgen05_fence_after();
 #pragma unroll 1
@@ -371,9 +390,10 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       }
       tcgen05_fence_before();
       mbar_arrive(&p_full[q]);
+      if (threadIdx.x == q * 128) TRACE_EV(q, 5, j);
     }
     // ---- epilogue: O[:, :d] / O[:, d] ----
-    mbar_wait(o_full, 0);
+    mbar_wait(&o_full[q], 0);
     tcgen05_fence_after();
     const int t = q_row0 + q * 128 + row;
     float inv_l;
@@ -428,7 +448,7 @@ static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, in
     configured = true;
   }
   dim3 grid((q_tiles + NQ - 1) / NQ, bh);
-  attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG><<<grid, NQ * 128 + 64, smem, stream>>>(tm, p);
+  attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG><<<grid, NQ * 128 + 32 + NQ * 32, smem, stream>>>(tm, p);
   TCL_CHECK_LAUNCH("tcl_attention");
   return TCL_OK;
 }
@@ -437,7 +457,8 @@ static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, in
 
 using namespace tcl;
 
-static int g_attn_variant = 0;
+static int g_attn_variant = 1;   // P through TMEM (fastest measured, profiles/r01_attention_v2_variants.txt)
+static long long* g_attn_trace = nullptr;
 
 extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
   TCL_CHECK_ARG(a != nullptr, "tcl_attention: null descriptor");
@@ -480,6 +501,7 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)a->d);
   p.out = a->out;
   p.out_pitch = (long long)a->heads * a->d;
+  p.trace = g_attn_trace;
   const int q_tiles = (a->tq + 127) / 128;
   const int var = g_attn_variant;
   if (a->d_pad == 64) {
@@ -505,8 +527,8 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
                 : launch_attn<1, 128, 2, 2, false>(tm, p, q_tiles, bh, stream);
   } else {
     if (var >= 1)
-      return bf16 ? launch_attn<1, 192, 2, 2, true, true>(tm, p, q_tiles, bh, stream)
-                  : launch_attn<1, 192, 2, 2, false, true>(tm, p, q_tiles, bh, stream);
+      return bf16 ? launch_attn<1, 192, 2, 1, true, true>(tm, p, q_tiles, bh, stream)
+                  : launch_attn<1, 192, 2, 1, false, true>(tm, p, q_tiles, bh, stream);
     return bf16 ? launch_attn<1, 192, 2, 1, true>(tm, p, q_tiles, bh, stream)
                 : launch_attn<1, 192, 2, 1, false>(tm, p, q_tiles, bh, stream);
   }
@@ -519,3 +541,8 @@ extern "C" int tcl_debug_attention_variant(int v) {
   g_attn_variant = v;
   return old;
 }
+
+// Debug hook (effective only in -DTCL_ATTN_TRACE builds): device buffer of 3*8*8 int64 receiving clock64 stamps of
+// CTA (0,0) for KV tiles 64..71: role 0/1 = softmax warpgroup q {wait S, got S, loaded S, exp done, got P-empty, P stored},
+// role 2 = MMA thread {q0: wait S-empty, got it, wait P-full, got it; q1: the same}.
+extern "C" void tcl_debug_attention_trace(long long* buf) { g_attn_trace = buf; }

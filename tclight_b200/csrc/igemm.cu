@@ -122,11 +122,11 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (converged warp, elected lane issues) =====================
+    {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
@@ -146,11 +146,14 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
             const int cy = y0 * sd.stride + dy - sd.pad;
             for (int cc = 0; cc < sd.cchunks; ++cc, ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* a_dst = smem + stage * STAGE_BYTES;
-              uint8_t* b_dst = a_dst + A_STAGE;
-              mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + B_STAGE);
-              tma_load_4d(a_dst, &tm.a[s], &full_bar[stage], cc * IG_BK, cx, cy, img0);
-              tma_load_2d(b_dst, &tm.b, &full_bar[stage], kb * IG_BK, nt * BN);
+              if (elect_one()) {
+                uint8_t* a_dst = smem + stage * STAGE_BYTES;
+                uint8_t* b_dst = a_dst + A_STAGE;
+                mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + B_STAGE);
+                tma_load_4d(a_dst, &tm.a[s], &full_bar[stage], cc * IG_BK, cx, cy, img0);
+                tma_load_2d(b_dst, &tm.b, &full_bar[stage], kb * IG_BK, nt * BN);
+              }
+              __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -159,10 +162,14 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the control flow converged and one elected lane issues: operands then live in uniform
+    // registers.  (Issuing from inside `if (lane == 0)` made the compiler wrap every tcgen05.mma in an
+    // ELECT / R2UR.BROADCAST waterfall, ~70 clk per instruction — more than a BN<=160 MMA takes to execute.)
+    {
       constexpr uint32_t idesc = umma_idesc_f16(BF16, IG_BM, BN);
       uint32_t stage = 0, phase = 0;
       uint32_t acc = 0, acc_phase = 0;
+      const uint32_t smem_base = smem_u32(smem);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
@@ -170,18 +177,21 @@ igemm_kernel(const __grid_constant__ IgTmaps tm, const __grid_constant__ IgParam
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t a_desc = umma_desc_k_sw128(a_addr);
-          const uint64_t b_desc = umma_desc_k_sw128(a_addr + A_STAGE);
+          if (elect_one()) {
+            const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
+            const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+            const uint64_t b_desc = umma_desc_k_sw128(a_addr + A_STAGE);
 #pragma unroll
-          for (int k = 0; k < IG_BK / 16; ++k) {
-            // advance 16 elements (32 B) inside the 128 B swizzle row: +2 in 16-byte units
-            umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < IG_BK / 16; ++k) {
+              // advance 16 elements (32 B) inside the 128 B swizzle row: +2 in 16-byte units
+              umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (kb + 1 == p.k_blocks) umma_commit(&tfull_bar[acc]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

