@@ -217,6 +217,8 @@ int tcl_gather_rows(int dtype, const void* x0, long long n0, const void* x1, lon
  * l1_loss / relaxed_ms_ssim(start_level=1, data_range=1) / TVLoss (utils/loss_utils.py:25, 73-211,
  * 324-339), SH2RGB (utils/sh_utils.py:117-118), index_select + its index_add backward, and
  * torch.optim.Adam.step + zero_grad.
+ *   grad     : stage 2: [U,4] fp32, ZERO-FILLED once by the caller (a row is {dR, dG, dB, padding} so that every
+ *              scatter is one 16-byte reduction); stage 1: [N,12].  The calls leave it zeroed.
  *   idx_host : HOST array of the batch's frame indices (what the DataLoader's sampler drew)
  *   ids      : unq_inv as int32 [N*H*W] (data_parser.unq_inv, video_dataparser.py:59)
  *   loss_out : device float[3] = {loss, loss_flow, loss_photometric} of this iteration (or NULL)
@@ -258,6 +260,9 @@ int tcl_exposure_gradient(const tcl_postopt_ctx* ctx, const int* idx_host, int n
                           float* loss_out, tcl_stream_t stream);
 int tcl_adam_step(float* p, float* grad, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                   int step, tcl_stream_t stream);
+/* the same for the UVT rows: fdc, m, v are [U,3], grad4 is the [U,4] gradient of tcl_uvt_gradient */
+int tcl_adam_step_uvt(float* fdc, float* grad4, float* m, float* v, long long U, float lr, float beta1, float beta2,
+                      float eps, int step, tcl_stream_t stream);
 /* generate.py:477-479: fdc = RGB2SH(scatter_mean(edited, unq_inv)); cnt_ws = U floats of scratch */
 int tcl_uvt_init(const float* edited, const int* ids, int N, int H, int W, long long U, float* fdc, float* cnt_ws,
                  tcl_stream_t stream);

@@ -268,3 +268,6 @@ lib.tcl_unique_inverse_workspace_bytes.restype = C.c_size_t
 lib.tcl_unique_inverse.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                    C.c_void_p]
 lib.tcl_unique_inverse.restype = C.c_int
+lib.tcl_adam_step_uvt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float,
+                                  C.c_float, C.c_int, C.c_void_p]
+lib.tcl_adam_step_uvt.restype = C.c_int

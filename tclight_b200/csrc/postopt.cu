@@ -357,6 +357,12 @@ __device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
   c[0] = cubic2(t + 1.f); c[1] = cubic1(t); c[2] = cubic1(1.f - t); c[3] = cubic2((1.f - t) + 1.f);
 }
 
+// one 16-byte reduction instead of three scalar ones (REDG.E.ADD.F32x4): the predecessor-gradient image and the UVT
+// gradient keep 4 floats per pixel / row for this (lane 3 is padding)
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(0.f) : "memory");
+}
+
 struct L0Params {
   int H, W;
   long long P;
@@ -371,10 +377,10 @@ struct L0Params {
   float k_tvh, k_tvw;             // lambda_tv*2/(count_h*n), lambda_tv*2/(count_w*n)
   float k_l1;                     // stage 1: (1-lambda_flow)*(1-lambda_dssim)/(n*3*P); 0 in stage 2
   const float* edited;            // [N,3,P] (stage 1 L1 target and affine input)
-  float* G_pre;                   // [n,3,P] atomically accumulated predecessor gradient
+  float* G_pre;                   // [n,P,4] atomically accumulated predecessor gradient (lane 3 unused)
   float* scal;
   // sinks
-  const int* ids; float* grad_fdc;        // stage 2
+  const int* ids; float* grad_fdc;        // stage 2: [U,4] (lane 3 unused)
   float* grad_expo;                       // stage 1: [N,12]
 };
 
@@ -438,20 +444,20 @@ level0_kernel(L0Params q) {
         s[c] = sg * m * q.k_flow;
         g[c] -= s[c];
       }
-      float* Gp = q.G_pre + (long long)b * 3 * q.P;
+      float* Gp = q.G_pre + (long long)b * 4 * q.P;
+      if (s[0] != 0.f || s[1] != 0.f || s[2] != 0.f) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int yy = y0 + j;
-        if (yy < 0 || yy >= q.H) continue;
+        for (int j = 0; j < 4; ++j) {
+          const int yy = y0 + j;
+          if (yy < 0 || yy >= q.H) continue;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int xx = x0 + i;
-          if (xx < 0 || xx >= q.W) continue;
-          const float wgt = cx[i] * cy[j];
-          const long long o = (long long)yy * q.W + xx;
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-            if (s[c] != 0.f) atomicAdd(&Gp[c * q.P + o], s[c] * wgt);
+          for (int i = 0; i < 4; ++i) {
+            const int xx = x0 + i;
+            if (xx < 0 || xx >= q.W) continue;
+            const float wgt = cx[i] * cy[j];
+            const long long o = (long long)yy * q.W + xx;
+            red_add_v4(Gp + o * 4, s[0] * wgt, s[1] * wgt, s[2] * wgt);
+          }
         }
       }
     }
@@ -492,9 +498,9 @@ level0_kernel(L0Params q) {
     const unsigned char fl = q.flags[(long long)b * q.P + p];
     if (MODE == 0) {
       const int id = q.ids[(long long)fr * q.P + p];
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-        if ((fl >> c) & 1) atomicAdd(&q.grad_fdc[(long long)id * 3 + c], g[c] * SH_C0);
+      if (fl & 7)
+        red_add_v4(q.grad_fdc + (long long)id * 4, (fl & 1) ? g[0] * SH_C0 : 0.f, (fl & 2) ? g[1] * SH_C0 : 0.f,
+                   (fl & 4) ? g[2] * SH_C0 : 0.f);
     } else {
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
@@ -538,18 +544,18 @@ pre_sink_kernel(L0Params q) {
 #pragma unroll
   for (int k = 0; k < 12; ++k) ge[k] = 0.f;
   if (MODE == 1 && threadIdx.x < 12) eg[threadIdx.x] = 0.f;
-  float* Gp = q.G_pre + (long long)b * 3 * q.P;
+  float4* Gp = reinterpret_cast<float4*>(q.G_pre + (long long)b * 4 * q.P);
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < q.P; p += (long long)gridDim.x * blockDim.x) {
-    float g[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { g[c] = Gp[c * q.P + p]; Gp[c * q.P + p] = 0.f; }
-    if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) continue;
+    const float4 gv = Gp[p];
+    if (gv.x == 0.f && gv.y == 0.f && gv.z == 0.f) continue;
+    Gp[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float g[3] = {gv.x, gv.y, gv.z};
     const unsigned char fl = q.flags[(long long)(q.bt.n + b) * q.P + p];
     if (MODE == 0) {
       const int id = q.ids[(long long)fr * q.P + p];
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-        if ((fl >> c) & 1) atomicAdd(&q.grad_fdc[(long long)id * 3 + c], g[c] * SH_C0);
+      if (fl & 7)
+        red_add_v4(q.grad_fdc + (long long)id * 4, (fl & 1) ? g[0] * SH_C0 : 0.f, (fl & 2) ? g[1] * SH_C0 : 0.f,
+                   (fl & 4) ? g[2] * SH_C0 : 0.f);
     } else {
       float in[3];
 #pragma unroll
@@ -610,6 +616,58 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
     la.loss_out[0] = (1.f - la.lambda_flow) * photo + la.lambda_flow * flow + tv;
     la.loss_out[1] = flow;
     la.loss_out[2] = photo;
+  }
+}
+
+// Stage-2 Adam over the UVT rows: p, m, v are [U,3], the gradient is [U,4] (lane 3 padding).  One thread handles four
+// rows = three float4 of p/m/v and four float4 of g, so every access is a 16-byte vector.
+__global__ void __launch_bounds__(256)
+adam_uvt_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long U,
+                float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt) {
+  const float step_size = lr / bc1;
+  const long long quads = U / 4;
+  auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+    mi = mi + (gi - mi) * (1.f - beta1);
+    vi = vi * beta2 + (1.f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi = pi - step_size * (mi / denom);
+  };
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < quads; t += (long long)gridDim.x * blockDim.x) {
+    float4* p4 = reinterpret_cast<float4*>(p) + t * 3;
+    float4* m4 = reinterpret_cast<float4*>(m) + t * 3;
+    float4* v4 = reinterpret_cast<float4*>(v) + t * 3;
+    float4* g4 = reinterpret_cast<float4*>(g) + t * 4;
+    float pa[12], ma[12], va[12], ga[12];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float4 a = p4[k], b = m4[k], c = v4[k];
+      pa[4 * k] = a.x; pa[4 * k + 1] = a.y; pa[4 * k + 2] = a.z; pa[4 * k + 3] = a.w;
+      ma[4 * k] = b.x; ma[4 * k + 1] = b.y; ma[4 * k + 2] = b.z; ma[4 * k + 3] = b.w;
+      va[4 * k] = c.x; va[4 * k + 1] = c.y; va[4 * k + 2] = c.z; va[4 * k + 3] = c.w;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float4 a = g4[r];
+      ga[3 * r] = a.x; ga[3 * r + 1] = a.y; ga[3 * r + 2] = a.z;
+      g4[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) upd(pa[k], ga[k], ma[k], va[k]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      p4[k] = make_float4(pa[4 * k], pa[4 * k + 1], pa[4 * k + 2], pa[4 * k + 3]);
+      m4[k] = make_float4(ma[4 * k], ma[4 * k + 1], ma[4 * k + 2], ma[4 * k + 3]);
+      v4[k] = make_float4(va[4 * k], va[4 * k + 1], va[4 * k + 2], va[4 * k + 3]);
+    }
+  }
+  // tail rows (U % 4)
+  if (blockIdx.x == 0 && threadIdx.x < 3 * (int)(U - quads * 4)) {
+    const long long row = quads * 4 + threadIdx.x / 3;
+    const int c = threadIdx.x % 3;
+    const long long i = row * 3 + c;
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(pi, g[row * 4 + c], mi, vi);
+    p[i] = pi; m[i] = mi; v[i] = vi; g[row * 4 + c] = 0.f;
   }
 }
 
@@ -693,7 +751,7 @@ static size_t ws_bytes(int H, int W, int nb) {
   size_t b = 0;
   b += align_up(sizeof(float) * 2 * nb * 3 * P);          // X
   b += align_up((size_t)2 * nb * P);                      // flags
-  b += align_up(sizeof(float) * nb * 3 * P);              // G_pre
+  b += align_up(sizeof(float) * nb * 4 * P);              // G_pre [nb,P,4]
   b += align_up(sizeof(float) * nb * 3 * py.total);       // X pyramid levels 1..4
   b += align_up(sizeof(float) * nb * 3 * py.total);       // dX pyramid
   b += align_up(sizeof(float) * 4 * nb * 3 * 2);          // sums
@@ -707,7 +765,7 @@ static void carve(void* base, int H, int W, int nb, Ws* w) {
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   w->X = (float*)p; p += align_up(sizeof(float) * 2 * nb * 3 * P);
   w->flags = p; p += align_up((size_t)2 * nb * P);
-  w->G_pre = (float*)p; p += align_up(sizeof(float) * nb * 3 * P);
+  w->G_pre = (float*)p; p += align_up(sizeof(float) * nb * 4 * P);
   w->xpyr = (float*)p; p += align_up(sizeof(float) * nb * 3 * py.total);
   w->dpyr = (float*)p; p += align_up(sizeof(float) * nb * 3 * py.total);
   w->sums = (float*)p; p += align_up(sizeof(float) * 4 * nb * 3 * 2);
@@ -847,7 +905,11 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
     // gradient only (data parallel: the caller all-reduces grad, then calls tcl_adam_step): n = 0 elements,
     // the single block just assembles this rank's share of the loss
     adam_kernel<<<1, 32, 0, stream>>>(nullptr, nullptr, nullptr, nullptr, 0, 0.f, beta1, beta2, eps, 1.f, 1.f, la);
-  } else if (stage == 2) adam_kernel<<<gridp(U * 3, 256, 148 * 16), 256, 0, stream>>>(fdc, grad, m, v, U * 3, lr, beta1, beta2, eps, bc1, bc2_sqrt, la);
+  } else if (stage == 2) {
+    adam_uvt_kernel<<<gridp(U / 4 + 1, 256, 148 * 16), 256, 0, stream>>>(fdc, grad, m, v, U, lr, beta1, beta2, eps, bc1, bc2_sqrt);
+    TCL_CHECK_LAUNCH("postopt adam");
+    adam_kernel<<<1, 32, 0, stream>>>(nullptr, nullptr, nullptr, nullptr, 0, 0.f, beta1, beta2, eps, 1.f, 1.f, la);   // loss assembly
+  }
   else adam_kernel<<<gridp((long long)c->N * 12, 256), 256, 0, stream>>>(expo, egrad, em, ev, (long long)c->N * 12, lr, beta1, beta2, eps, bc1, bc2_sqrt, la);
   TCL_CHECK_LAUNCH("postopt(adam)");
   return TCL_OK;
@@ -951,5 +1013,16 @@ extern "C" int tcl_adam_step(float* p, float* grad, float* m, float* v, long lon
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   adam_kernel<<<gridp(n, 256, 148 * 16), 256, 0, stream>>>(p, grad, m, v, n, lr, beta1, beta2, eps, bc1, bc2_sqrt, la);
   TCL_CHECK_LAUNCH("tcl_adam_step");
+  return TCL_OK;
+}
+
+// Data-parallel stage 2: Adam over the UVT rows after the [U,4] gradient has been all-reduced.
+extern "C" int tcl_adam_step_uvt(float* fdc, float* grad4, float* m, float* v, long long U, float lr, float beta1, float beta2,
+                                 float eps, int step, cudaStream_t stream) {
+  TCL_CHECK_ARG(fdc && grad4 && m && v && U > 0 && step >= 1, "tcl_adam_step_uvt: args");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  adam_uvt_kernel<<<gridp(U / 4 + 1, 256, 148 * 16), 256, 0, stream>>>(fdc, grad4, m, v, U, lr, beta1, beta2, eps, bc1, bc2_sqrt);
+  TCL_CHECK_LAUNCH("tcl_adam_step_uvt");
   return TCL_OK;
 }

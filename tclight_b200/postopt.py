@@ -134,8 +134,12 @@ def _dp_iteration(stage, ctx, mine, n_global, n_valid_global, params, grad, m, v
             check(lib.tcl_exposure_gradient(C.byref(ctx.c), arr, nb, params.data_ptr(), grad.data_ptr(), loss_row.data_ptr(),
                                             stream_ptr()), "tcl_exposure_gradient")
     dist.all_reduce(grad)
-    check(lib.tcl_adam_step(params.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), params.numel(), lr, 0.9, 0.999, eps,
-                            step, stream_ptr()), "tcl_adam_step")
+    if stage == 2:
+        check(lib.tcl_adam_step_uvt(params.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), U, lr, 0.9, 0.999, eps,
+                                    step, stream_ptr()), "tcl_adam_step_uvt")
+    else:
+        check(lib.tcl_adam_step(params.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), params.numel(), lr, 0.9, 0.999,
+                                eps, step, stream_ptr()), "tcl_adam_step")
 
 
 def _idx_array(idxs) -> Tuple[C.Array, int]:
@@ -204,7 +208,8 @@ def unique_tensor_optimization(gen) -> Tuple[torch.Tensor, List[float]]:
     check(lib.tcl_uvt_init(ds.edited_images.data_ptr(), ids.data_ptr(), N, H, W, U, fdc.data_ptr(), cnt.data_ptr(), stream_ptr()),
           "tcl_uvt_init")
     del cnt
-    grad, m, v = (torch.zeros_like(fdc) for _ in range(3))
+    m, v = torch.zeros_like(fdc), torch.zeros_like(fdc)
+    grad = torch.zeros((U, 4), device=dev, dtype=torch.float32)     # {dR, dG, dB, pad}: one 16-byte reduction per scatter
     n_it = gen.epochs * ((N + Bo - 1) // Bo)
     losses = torch.zeros((n_it, 3), device=dev, dtype=torch.float32)
     step = 0
@@ -287,7 +292,8 @@ def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: i
     cnt = torch.empty(U, device=device, dtype=torch.float32)
     check(lib.tcl_uvt_init(ds.edited_images.data_ptr(), ids.data_ptr(), N, H, W, U, fdc.data_ptr(), cnt.data_ptr(), stream_ptr()), "tcl_uvt_init")
     del cnt
-    grad, m, v = (torch.zeros_like(fdc) for _ in range(3))
+    m, v = torch.zeros_like(fdc), torch.zeros_like(fdc)
+    grad = torch.zeros((U, 4), device=device, dtype=torch.float32)
     losses = torch.zeros((iters + 8, 3), device=device)
     gcpu = torch.Generator().manual_seed(0)
     lr = 0.05 * Bo / N

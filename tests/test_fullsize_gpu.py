@@ -118,7 +118,8 @@ def test_stage2_iteration_720p(cuda):
     ctx = P._Context(ds, 0.2, 0.8, 0.05, 3)
     ids = inv.to(torch.int32).contiguous()
     p = fdc0.clone()
-    g, m, v = (torch.zeros_like(p) for _ in range(3))
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    g = torch.zeros((p.shape[0], 4), device=cuda)        # UVT gradient rows are {dR, dG, dB, pad}
     lo = torch.zeros(3, device=cuda)
     arr = (C.c_int * 3)(*idx)
     check(lib.tcl_uvt_iteration(C.byref(ctx.c), arr, 3, ids.data_ptr(), size, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),

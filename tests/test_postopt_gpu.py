@@ -60,7 +60,8 @@ def test_stage2_gradient_matches_autograd(cuda, h, w, unique_rows):
     ctx = P._Context(ds, 0.2, 0.8, 0.05, 4)
     ids = inv.to(torch.int32).contiguous()
     p = fdc0.clone()
-    g, m, v = (torch.zeros_like(p) for _ in range(3))
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    g = torch.zeros((p.shape[0], 4), device=cuda)        # UVT gradient rows are {dR, dG, dB, pad}
     lo = torch.zeros(3, device=cuda)
     arr = (C.c_int * 4)(*idx)
     check(lib.tcl_uvt_iteration(C.byref(ctx.c), arr, 4, ids.data_ptr(), size, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
