@@ -22,10 +22,6 @@
 
 namespace tcl {
 
-#ifndef TCL_ATTN_POLY
-#define TCL_ATTN_POLY 0   // of every 8 exponentials, how many run as FMA-pipe polynomials (see poly_exp2)
-#endif
-
 struct AttnParams {
   int tq, tk;          // valid query / key rows per (batch, head)
   int heads, d;        // true head dim
@@ -79,6 +75,18 @@ __device__ __forceinline__ float poly_exp2(float x) {
   return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
 }
 
+// P (>= 0, finite) -> two 16-bit values in one register.  F2FP.PACK_AB executes on the XU pipe next to MUFU.EX2
+// (ncu: XU busy = MUFU + ~12 %), which is the binding pipe of this kernel; for bf16 the same result up to ties
+// (round half up instead of half to even) comes from two integer adds and one byte permute on the ALU pipe.
+template <bool BF16, bool IPACK>
+__device__ __forceinline__ uint32_t pack_p(float a, float b) {
+  if (BF16 && IPACK) {
+    const uint32_t ua = __float_as_uint(a) + 0x8000u, ub = __float_as_uint(b) + 0x8000u;
+    return __byte_perm(ua, ub, 0x7632);
+  }
+  return Elem<BF16>::pack(a, b);
+}
+
 // D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (P, 16-bit pairs packed in 32-bit TMEM columns, one row per
 // lane) is read straight from tensor memory, so P never crosses shared memory.
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
@@ -94,9 +102,10 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 }
 
 // TS   : P is handed to the P V MMA through TMEM (tcgen05.st + A-from-TMEM MMA) instead of swizzled smem.
-// POLY : of every 8 exponentials, how many run as FMA-pipe polynomials (poly_exp2) instead of MUFU.EX2.
+// POLY : 8-bit mask over every 8 consecutive exponentials: set bits run as FMA-pipe polynomials (poly_exp2)
+//        instead of MUFU.EX2.
 // STAG : softmax warpgroup q starts q*STAG clocks late, so the warpgroups' MUFU phases interleave.
-template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS, int POLY, int STAG>
+template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS, int POLY, int STAG, bool IPACK>
 __global__ void __launch_bounds__(NQ * 128 + 32 + NQ * 32, 1)
 attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnParams p) {
   using E = Elem<BF16>;
@@ -337,9 +346,9 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
         for (int i = 0; i < 32; i += 2) {
           const float a0 = fmaf(__uint_as_float(s[i]), p.scale_log2, -m_ref);
           const float a1 = fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_ref);
-          const float e0 = ((i & 7) < POLY) ? poly_exp2<BF16>(a0) : fast_exp2(a0);
-          const float e1 = (((i + 1) & 7) < POLY) ? poly_exp2<BF16>(a1) : fast_exp2(a1);
-          pk[(c0 + i) >> 1] = E::pack(e0, e1);
+          const float e0 = ((POLY >> (i & 7)) & 1) ? poly_exp2<BF16>(a0) : fast_exp2(a0);
+          const float e1 = ((POLY >> ((i + 1) & 7)) & 1) ? poly_exp2<BF16>(a1) : fast_exp2(a1);
+          pk[(c0 + i) >> 1] = pack_p<BF16, IPACK>(e0, e1);
         }
       };
       do_chunk(s0, 0);
@@ -433,13 +442,13 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
   }
 }
 
-template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS = false, int POLY = 0, int STAG = 0>
+template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS = false, int POLY = 0, int STAG = 0, bool IPACK = false>
 static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, int bh, cudaStream_t stream) {
   constexpr size_t smem = (size_t)NQ * 128 * DPAD * 2 + (size_t)KST * 128 * DPAD * 2 +
                           (size_t)VST * 2 * DPAD * 128 + (TS ? 0 : (size_t)NQ * 128 * 128 * 2) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG>,
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG, IPACK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_last_error("attention: cudaFuncSetAttribute(%zu B) failed: %s", smem, cudaGetErrorString(e));
@@ -448,7 +457,7 @@ static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, in
     configured = true;
   }
   dim3 grid((q_tiles + NQ - 1) / NQ, bh);
-  attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG><<<grid, NQ * 128 + 32 + NQ * 32, smem, stream>>>(tm, p);
+  attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG, IPACK><<<grid, NQ * 128 + 32 + NQ * 32, smem, stream>>>(tm, p);
   TCL_CHECK_LAUNCH("tcl_attention");
   return TCL_OK;
 }
@@ -457,7 +466,7 @@ static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, in
 
 using namespace tcl;
 
-static int g_attn_variant = 1;   // P through TMEM (fastest measured, profiles/r01_attention_v2_variants.txt)
+static int g_attn_variant = 2;   // P through TMEM + 2 of 8 exponentials on the FMA pipe (fastest measured, profiles/r01_attention_v2_variants.txt)
 static long long* g_attn_trace = nullptr;
 
 extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
@@ -510,13 +519,13 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
                       : launch_attn<2, 64, 3, 2, false>(tm, p, q_tiles, bh, stream);
     }
     switch (var) {
-      case 1: return launch_attn<2, 64, 4, 3, true, true, 0, 0>(tm, p, q_tiles, bh, stream);
-      case 2: return launch_attn<2, 64, 4, 3, true, true, 0, 1200>(tm, p, q_tiles, bh, stream);
-      case 3: return launch_attn<2, 64, 4, 3, true, true, 2, 0>(tm, p, q_tiles, bh, stream);
-      case 4: return launch_attn<2, 64, 4, 3, true, true, 3, 1200>(tm, p, q_tiles, bh, stream);
-      case 5: return launch_attn<2, 64, 3, 2, true, false, 0, 1200>(tm, p, q_tiles, bh, stream);
-      case 6: return launch_attn<2, 64, 4, 3, true, true, 2, 1200>(tm, p, q_tiles, bh, stream);
-      case 7: return launch_attn<2, 64, 4, 3, true, true, 0, 2000>(tm, p, q_tiles, bh, stream);
+      case 1: return launch_attn<2, 64, 4, 3, true, true, 0x00, 0>(tm, p, q_tiles, bh, stream);
+      case 2: return launch_attn<2, 64, 4, 3, true, true, 0x03, 0>(tm, p, q_tiles, bh, stream);
+      case 3: return launch_attn<2, 64, 4, 3, true, true, 0x11, 0>(tm, p, q_tiles, bh, stream);
+      case 4: return launch_attn<2, 64, 4, 3, true, true, 0x33, 0>(tm, p, q_tiles, bh, stream);
+      case 5: return launch_attn<2, 64, 4, 3, true, true, 0x0f, 0>(tm, p, q_tiles, bh, stream);
+      case 6: return launch_attn<2, 64, 4, 3, true, true, 0x13, 0>(tm, p, q_tiles, bh, stream);
+      case 7: return launch_attn<2, 64, 4, 3, true, true, 0x49, 0>(tm, p, q_tiles, bh, stream);
       default: return launch_attn<2, 64, 3, 2, true>(tm, p, q_tiles, bh, stream);
     }
   } else if (a->d_pad == 128) {
