@@ -59,6 +59,10 @@ typedef struct {
   int64_t pitch;   /* elements between consecutive pixels (>= c, multiple of 8) */
   int32_t taps;    /* 1 or 9 */
   int32_t stride;  /* 1 or 2: input coordinate = stride * output coordinate + tap - pad */
+  int32_t no_lead_pad; /* 3x3 only: 0 = zero padding 1 on every side; 1 = no padding before the first row/column,
+                          zero fill after the last (the F.pad(x, (0,1,0,1)) + stride-2 conv of the VAE encoder's
+                          Downsample2D) */
+  int32_t reserved_;
 } tcl_igemm_src;
 
 typedef struct {
@@ -178,6 +182,19 @@ int tcl_dpm_step(int latent_dtype, const void* eps, const void* x, const void* x
  * sampling: the two pairs swapped.  Each tensor op rounds to the latent dtype like the reference expression. */
 int tcl_ddim_next(int latent_dtype, const void* eps, const void* x, void* x_out, long long n, float mu_in, float sig_in,
                   float mu_out, float sig_out, tcl_stream_t stream);
+
+/* ---- VAE support (HBM-bound; utils/VidToMe/generate_utils.py:140-172) -------------------
+ * softmax_rows : in-place softmax over the first `cols` entries of every row of a 16-bit [rows, pitch] matrix
+ *                (entries cols..pitch-1 are set to 0): the key axis of AutoencoderKL's single-head mid-block attention,
+ *                whose scores come from tcl_igemm.
+ * image_to_nhwc: out[b, y, x, c] = src[b, c, y, x] * scale + shift for c < C, 0 for C <= c < c_pad
+ *                (src_dtype / out_dtype are TCL_LATENT_* codes); nhwc_to_image is the inverse with an optional clamp.
+ */
+int tcl_softmax_rows(int dtype, void* x, long long rows, int cols, int pitch, tcl_stream_t stream);
+int tcl_image_to_nhwc(int dtype, int src_dtype, const void* src, int B, int C, int H, int W, int c_pad, float scale,
+                      float shift, void* out, tcl_stream_t stream);
+int tcl_nhwc_to_image(int dtype, const void* in, int B, int C, int H, int W, int pitch, float scale, float shift,
+                      int do_clamp, float lo, float hi, int out_dtype, void* out, tcl_stream_t stream);
 
 /* ---- VidToMe token merging ------------------------------------------------------------------
  * bipartite_soft_matching_randframe (utils/VidToMe/vidtome/merge.py:20-159) and

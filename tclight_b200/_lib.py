@@ -34,6 +34,8 @@ class IgemmSrc(C.Structure):
         ("pitch", C.c_int64),
         ("taps", C.c_int32),
         ("stride", C.c_int32),
+        ("no_lead_pad", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 
@@ -271,3 +273,12 @@ lib.tcl_unique_inverse.restype = C.c_int
 lib.tcl_adam_step_uvt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_int, C.c_void_p]
 lib.tcl_adam_step_uvt.restype = C.c_int
+
+lib.tcl_softmax_rows.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]
+lib.tcl_softmax_rows.restype = C.c_int
+lib.tcl_image_to_nhwc.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                  C.c_void_p, C.c_void_p]
+lib.tcl_image_to_nhwc.restype = C.c_int
+lib.tcl_nhwc_to_image.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
+                                  C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+lib.tcl_nhwc_to_image.restype = C.c_int

@@ -551,7 +551,7 @@ extern "C" int tcl_igemm(const tcl_igemm_desc* d, cudaStream_t stream) {
     p.src[s].taps = S.taps;
     p.src[s].cchunks = (int)(S.c / IG_BK);
     p.src[s].stride = S.stride;
-    p.src[s].pad = S.taps == 9 ? 1 : 0;
+    p.src[s].pad = (S.taps == 9 && !S.no_lead_pad) ? 1 : 0;
     ktot += (long long)S.taps * S.c;
     const uint64_t dims[4] = {(uint64_t)S.c, (uint64_t)S.w, (uint64_t)S.h, (uint64_t)S.n};
     const uint64_t strides[3] = {(uint64_t)S.pitch * 2, (uint64_t)S.w * S.pitch * 2,

@@ -88,7 +88,7 @@ def igemm(
 ) -> Optional[torch.Tensor]:
     """out[pixel, n] = sum_k A[pixel, k] W[n, k]  (tcgen05 implicit GEMM).
 
-    srcs      : [(NHWC tensor [n,h,w,c], taps (1|9), stride (1|2)), ...] — K segments in order
+    srcs      : [(NHWC tensor [n,h,w,c], taps (1|9), stride (1|2)[, no_lead_pad]), ...] — K segments in order
     weight    : [N, K] 16-bit, K = sum(taps*c)
     out_grid  : (n_img, out_h, out_w)
     heads     : for TCL_EPI_HEADS: dict(sec=[(tensor, is_vt), ...], heads=, d=, d_pad=,
@@ -99,7 +99,8 @@ def igemm(
     d.dtype = dtype_code(dt)
     d.num_src = len(srcs)
     ktot = 0
-    for i, (t, taps, stride) in enumerate(srcs):
+    for i, src in enumerate(srcs):
+        t, taps, stride = src[:3]
         require_cuda(t)
         if t.dtype != dt or t.dim() != 4:
             raise TclError(f"igemm source {i}: need 4-D NHWC {dt}, got {tuple(t.shape)} {t.dtype}")
@@ -109,6 +110,7 @@ def igemm(
         s.pitch = _pixel_pitch(t)
         s.taps = taps
         s.stride = stride
+        s.no_lead_pad = int(len(src) > 3 and bool(src[3]))
         ktot += taps * t.shape[3]
     N = weight.shape[0]
     if weight.dim() != 2 or weight.shape[1] != ktot or not weight.is_contiguous():
@@ -152,7 +154,7 @@ def igemm(
             d.residual = residual.data_ptr()
             d.res_pitch = residual.stride(-2)
         ret = out
-    with _Prof("igemm_conv3x3" if any(tp == 9 for _, tp, _ in srcs) else "igemm_linear", 2.0 * n_img * oh * ow * N * ktot):
+    with _Prof("igemm_conv3x3" if any(sr[1] == 9 for sr in srcs) else "igemm_linear", 2.0 * n_img * oh * ow * N * ktot):
         check(lib.tcl_igemm(C.byref(d), stream_ptr()), "tcl_igemm")
     return ret
 

@@ -136,3 +136,62 @@ def test_random_state_dict_has_diffusers_sd15_layout():
     assert p.shape == (2, 27) and p[1, (1 * 3 + 2) * 3 + 0] == w[1, 0, 1, 2]
     wi, bi = interleave_geglu(torch.arange(512.)[:, None].repeat(1, 2), torch.arange(512.))
     assert wi[0, 0] == 0 and wi[128, 0] == 256 and wi[256, 0] == 128 and bi[384] == 384
+
+
+def test_new_mirrors_refuse_cpu_tensors():
+    """flow_utils / invert / vae are CUDA-only product paths (no CPU fallback)."""
+    import types
+
+    import pytest
+    import torch
+    from tclight_b200 import flow_utils
+    from tclight_b200._lib import TclError
+    from tclight_b200.invert import Inverter
+    from tclight_b200.scheduler import DDIMSchedulerB200
+    from tclight_b200.vae import AutoencoderKLB200
+
+    x = torch.zeros(2, 3, 16, 16)
+    f = torch.zeros(2, 2, 16, 16)
+    with pytest.raises(TclError):
+        flow_utils.warp_flow(x, f)
+    with pytest.raises(TclError):
+        flow_utils.get_soft_mask_bwds(x, f, f)
+    with pytest.raises(TclError):
+        flow_utils.get_flowid(x, f, torch.ones(2, 1, 16, 16))
+    with pytest.raises(TclError):
+        flow_utils.voxelization(torch.zeros(8, 1, dtype=torch.int32))
+    with pytest.raises(TclError):
+        AutoencoderKLB200({}, device="cpu")
+
+    class D(dict):
+        __getattr__ = dict.__getitem__
+
+    cfg = types.SimpleNamespace(device="cuda", sd_version="1.5", model_key=None, float_precision="fp16", height=64, width=64,
+                                inversion=D(control="none", control_scale=1.0, save_steps=5, steps=5, prompt="", recon=False,
+                                            save_intermediate=False, use_blip=False, batch_size=8, force=True, n_frames=None))
+    inv = Inverter(types.SimpleNamespace(unet=None), DDIMSchedulerB200(), cfg)
+    assert list(inv.scheduler.timesteps) == [801, 601, 401, 201, 1]
+    mu, sg, mu_p, sg_p = inv._coefs(801, 0, False)
+    assert abs(mu * mu + sg * sg - 1) < 1e-6 and abs(mu_p * mu_p + sg_p * sg_p - 1) < 1e-6 and mu_p > mu
+    with pytest.raises(TclError):
+        inv.pred_next_x(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8), 801, 0)
+    cfg.inversion["control"] = "depth"
+    with pytest.raises(TclError):
+        Inverter(types.SimpleNamespace(unet=None), DDIMSchedulerB200(), cfg)
+
+
+def test_vae_oracle_shapes():
+    import torch
+    from oracle import vae_ref as V
+
+    m = V.make_vae(block_out_channels=(64, 64, 128, 128))
+    keys = set(m.state_dict().keys())
+    for k in ("encoder.down_blocks.0.downsamplers.0.conv.weight", "decoder.up_blocks.2.upsamplers.0.conv.weight",
+              "encoder.mid_block.attentions.0.to_q.weight", "decoder.mid_block.attentions.0.to_out.0.bias",
+              "quant_conv.weight", "post_quant_conv.bias", "decoder.up_blocks.3.resnets.0.conv_shortcut.weight" if False else "decoder.conv_norm_out.weight"):
+        assert k in keys, k
+    x = torch.rand(1, 3, 40, 56)
+    z = V.encode_imgs(m, x)
+    assert z.shape == (1, 4, 5, 7)
+    y = V.decode_latents(m, z)
+    assert y.shape == x.shape and 0 <= float(y.min()) and float(y.max()) <= 1
