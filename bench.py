@@ -288,9 +288,12 @@ def run_b200(args):
     roof = None
     if a["ms"] > 0:
         ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "attn_kernel<NQ=2,DPAD=64> (ds-1 self/cross attention)", "achieved": ach,
+        roof = {"bound": "tensor", "kernel": "attn_kernel<NQ=2,DPAD=64,TS,POLY=0x03> (ds-1 self/cross attention)", "achieved": ach,
                 "peak": pk["bf16_tflops_sustained"], "peak_kind": f"{pk_kind} sustained bf16", "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+                "frac": ach / pk["bf16_tflops_sustained"],
+                # dram__bytes_read+write of ONE launch of this kernel at its largest shape (ds-1 merged xy self-attention,
+                # B*H=16, T=47 520): profiles/r01_attention_v2_ncu_summary.md; algorithmic Q,K,V^T,O bytes of that launch: 353 MB
+                "traffic": 347.0e6, "traffic_unit": "bytes/launch (ncu --set full, largest launch shape)",
                 "launches": a["launches"], "avg_launch_ms": a["ms"] / max(1, a["launches"]),
                 "share_of_step": a["ms"] / ms}
     total_fl = sum(v["flops"] for v in prof.values())

@@ -105,8 +105,11 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 // POLY : 8-bit mask over every 8 consecutive exponentials: set bits run as FMA-pipe polynomials (poly_exp2)
 //        instead of MUFU.EX2.
 // STAG : softmax warpgroup q starts q*STAG clocks late, so the warpgroups' MUFU phases interleave.
-template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS, int POLY, int STAG, bool IPACK>
-__global__ void __launch_bounds__(NQ * 128 + 32 + NQ * 32, 1)
+// SPLIT: softmax warpgroups per Q tile.  With 2, each thread owns one row x 64 score columns and the two halves
+//        exchange their row maxima through shared memory: 4 softmax warps per scheduler instead of 2 keep the XU
+//        pipe (MUFU.EX2 + F2FP, the binding pipe) busy while other warps sit in their load / max / store phases.
+template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS, int POLY, int STAG, bool IPACK, int SPLIT>
+__global__ void __launch_bounds__(NQ * 128 * SPLIT + 32 + NQ * 32, 1)
 attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnParams p) {
   using E = Elem<BF16>;
   constexpr int NC = DPAD / 64;                    // 64-wide chunks of the head dim
@@ -123,7 +126,9 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
   constexpr uint32_t TMEM_NEED = NQ * (128 + DPAD + (TS ? 64 : 0));
   static_assert(TMEM_NEED <= 512, "TMEM budget");
   constexpr uint32_t TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
-  constexpr int SOFT_THREADS = NQ * 128;
+  constexpr int SOFT_THREADS = NQ * 128 * SPLIT;
+  constexpr int COLS = 128 / SPLIT;                // score columns per softmax thread
+  static_assert(SPLIT == 1 || (SPLIT == 2 && TS), "column split needs P in TMEM");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -140,6 +145,7 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
   uint64_t* p_empty = p_full + NQ;          // NQ
   uint64_t* o_full = p_empty + NQ;          // NQ
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + NQ);
+  float* xch = reinterpret_cast<float*>(smem + OFF_BAR + 256);      // [2 parity][NQ][SPLIT][128] row maxima (SPLIT == 2)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -158,8 +164,8 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
     for (int i = 0; i < VST; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], NQ); }
     for (int i = 0; i < NQ; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&s_empty[i], 128 * SPLIT);
+      mbar_init(&p_full[i], 128 * SPLIT);
       mbar_init(&p_empty[i], 1);
       mbar_init(&o_full[i], 1);
     }
@@ -279,14 +285,16 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
     }
   } else {
     // ===================== softmax warpgroups =====================
-    const int q = warp >> 2;               // which Q tile
+    const int q = warp / (4 * SPLIT);        // which Q tile
+    const int half = (warp >> 2) % SPLIT;    // which column range of the score tile
     const int row = (warp & 3) * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const uint32_t t_s = t_lane + q * 128;
+    const uint32_t t_s = t_lane + q * 128 + half * COLS;
     const uint32_t t_o = t_lane + NQ * 128 + q * DPAD;
     float m_ref = -INFINITY;                 // reference max (scaled, log2 domain) used by exp2
     const uint32_t p_tile_addr = smem_u32(smem + OFF_P + (TS ? 0 : q * P_TILE));
-    const uint32_t t_p = t_lane + TMEM_P + q * 64;
+    const uint32_t t_p = t_lane + TMEM_P + q * 64 + half * (COLS / 2);
+    const bool tracer = threadIdx.x == q * 128 * SPLIT;
     if (STAG > 0 && q > 0) {
       const long long t0 = clock64();
       while (clock64() - t0 < (long long)STAG * q) {}
@@ -296,40 +304,58 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
     // blocking wait only runs when the early probe failed.
     bool s_ready = false;
     for (int j = 0; j < n_kv; ++j) {
-      if (threadIdx.x == q * 128) TRACE_EV(q, 0, j);
+      if (tracer) TRACE_EV(q, 0, j);
       if (!s_ready) mbar_wait(&s_full[q], j & 1);
-      if (threadIdx.x == q * 128) TRACE_EV(q, 1, j);
+      if (tracer) TRACE_EV(q, 1, j);
       tcgen05_fence_after();
       uint32_t s0[32], s1[32], s2[32], s3[32];
       tmem_ld_32x32b_x32(t_s + 0, s0);
       tmem_ld_32x32b_x32(t_s + 32, s1);
-      tmem_ld_32x32b_x32(t_s + 64, s2);
-      tmem_ld_32x32b_x32(t_s + 96, s3);
+      if constexpr (SPLIT == 1) {
+        tmem_ld_32x32b_x32(t_s + 64, s2);
+        tmem_ld_32x32b_x32(t_s + 96, s3);
+      }
       const bool pe_ready = mbar_test_wait(&p_empty[q], (j & 1) ^ 1);   // P V of the previous tile: consumed after the exps
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(&s_empty[q]);
-      if (threadIdx.x == q * 128) TRACE_EV(q, 2, j);
-      const int valid_cols = p.tk - j * 128;
-      const bool tail = valid_cols < 128;      // warp-uniform: only the last KV tile
+      if (tracer) TRACE_EV(q, 2, j);
+      const int valid_cols = p.tk - j * 128 - half * COLS;
+      const bool tail = valid_cols < COLS;      // warp-uniform: only the last KV tile
       if (tail) {
         auto mask = [&](uint32_t (&s)[32], int c0) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (c0 + i >= valid_cols) s[i] = 0xff800000u;   // -inf
         };
-        mask(s0, 0); mask(s1, 32); mask(s2, 64); mask(s3, 96);
+        mask(s0, 0); mask(s1, 32);
+        if constexpr (SPLIT == 1) { mask(s2, 64); mask(s3, 96); }
       }
-      // four independent max chains (a single 128-long dependent chain costs ~500 clk)
+      // independent max chains (a single 128-long dependent chain costs ~500 clk)
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
-        mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
-        mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
+      for (int i = 0; i < 32; i += SPLIT) {
+        if constexpr (SPLIT == 1) {
+          mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
+          mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
+          mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
+        } else {
+          mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(s0[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s1[i]));
+          mx3 = fmaxf(mx3, __uint_as_float(s1[i + 1]));
+        }
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      if constexpr (SPLIT == 2) {
+        // row maximum over both column halves: exchange through shared memory (double-buffered by tile parity; the
+        // named barrier of tile j+1 orders every read of tile j before any write of tile j+2)
+        float* slot = xch + (((j & 1) * NQ + q) * SPLIT) * 128;
+        slot[half * 128 + row] = mx;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + q) : "memory");
+        mx = fmaxf(mx, slot[(half ^ 1) * 128 + row]);
+      }
       const float m_new = mx * p.scale_log2;
       float factor = 1.f;
       if (j == 0) {
@@ -340,7 +366,7 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       }
       // 3 of every 8 exponentials run as polynomials on the FMA pipe, 5 on MUFU.EX2 (16 lanes/clk/SM is the
       // binding pipe of this kernel; the split balances the two pipes)
-      uint32_t pk[64];
+      uint32_t pk[COLS / 2];
       auto do_chunk = [&](uint32_t (&s)[32], int c0) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -353,19 +379,21 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       };
       do_chunk(s0, 0);
       do_chunk(s1, 32);
-      do_chunk(s2, 64);
-      do_chunk(s3, 96);
+      if constexpr (SPLIT == 1) {
+        do_chunk(s2, 64);
+        do_chunk(s3, 96);
+      }
       // the previous P V MMA must be done before P or O are touched.  Waiting here (not before the exponentials)
       // gives it the whole softmax of this tile to complete: the ncu source view of the earlier placement showed
       // a third of all stall samples on this barrier.
-      if (threadIdx.x == q * 128) TRACE_EV(q, 3, j);
+      if (tracer) TRACE_EV(q, 3, j);
       s_ready = (j + 1 < n_kv) && mbar_test_wait(&s_full[q], (j + 1) & 1);   // next scores: consumed at the loop top
       if (!pe_ready) mbar_wait(&p_empty[q], (j & 1) ^ 1);
-      if (threadIdx.x == q * 128) TRACE_EV(q, 4, j);
+      if (tracer) TRACE_EV(q, 4, j);
       if (__any_sync(0xffffffffu, factor != 1.f)) {
         tcgen05_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < DPAD; c0 += 32) {
+        for (int c0 = half * (DPAD / SPLIT); c0 < (half + 1) * (DPAD / SPLIT); c0 += 32) {
           uint32_t o[32];
           tmem_ld_32x32b_x32(t_o + c0, o);
           tmem_ld_wait();
@@ -378,13 +406,15 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       if (TS) {
         // P -> TMEM: lane = row, 32-bit column c holds keys (2c, 2c+1) — the K-major A operand of the P V MMA
         uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[0]);
-        uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
         tmem_st_32x32b_x32(t_p, lo);
-        tmem_st_32x32b_x32(t_p + 32, hi);
+        if constexpr (SPLIT == 1) {
+          uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
+          tmem_st_32x32b_x32(t_p + 32, hi);
+        }
         tmem_st_wait();
       } else {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 2 / SPLIT; ++c) {
           const uint32_t rowa = p_tile_addr + c * 16384 + row * 128;
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
@@ -399,7 +429,7 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       }
       tcgen05_fence_before();
       mbar_arrive(&p_full[q]);
-      if (threadIdx.x == q * 128) TRACE_EV(q, 5, j);
+      if (tracer) TRACE_EV(q, 5, j);
     }
     // ---- epilogue: O[:, :d] / O[:, d] ----
     mbar_wait(&o_full[q], 0);
@@ -419,7 +449,7 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
     typename E::T* out = reinterpret_cast<typename E::T*>(p.out) +
                          (static_cast<long long>(b) * p.tq + t) * p.out_pitch + head * p.d;
 #pragma unroll 1
-    for (int c0 = 0; c0 < p.d; c0 += 16) {
+    for (int c0 = half * 16; c0 < p.d; c0 += 16 * SPLIT) {     // the column halves share the output chunks
       uint32_t v[16];
       tmem_ld_32x32b_x16(t_o + c0, v);
       tmem_ld_wait();
@@ -442,13 +472,13 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
   }
 }
 
-template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS = false, int POLY = 0, int STAG = 0, bool IPACK = false>
+template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS = false, int POLY = 0, int STAG = 0, bool IPACK = false, int SPLIT = 1>
 static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, int bh, cudaStream_t stream) {
   constexpr size_t smem = (size_t)NQ * 128 * DPAD * 2 + (size_t)KST * 128 * DPAD * 2 +
-                          (size_t)VST * 2 * DPAD * 128 + (TS ? 0 : (size_t)NQ * 128 * 128 * 2) + 1024 + 256;
+                          (size_t)VST * 2 * DPAD * 128 + (TS ? 0 : (size_t)NQ * 128 * 128 * 2) + 1024 + 256 + 4096;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG, IPACK>,
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG, IPACK, SPLIT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_last_error("attention: cudaFuncSetAttribute(%zu B) failed: %s", smem, cudaGetErrorString(e));
@@ -457,7 +487,7 @@ static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, in
     configured = true;
   }
   dim3 grid((q_tiles + NQ - 1) / NQ, bh);
-  attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG, IPACK><<<grid, NQ * 128 + 32 + NQ * 32, smem, stream>>>(tm, p);
+  attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG, IPACK, SPLIT><<<grid, NQ * 128 * SPLIT + 32 + NQ * 32, smem, stream>>>(tm, p);
   TCL_CHECK_LAUNCH("tcl_attention");
   return TCL_OK;
 }
@@ -515,26 +545,33 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
   const int var = g_attn_variant;
   if (a->d_pad == 64) {
     if (!bf16) {
+      if (var >= 3) return launch_attn<2, 64, 4, 3, false, true, 0, 0, false, 2>(tm, p, q_tiles, bh, stream);
       return var >= 1 ? launch_attn<2, 64, 4, 3, false, true>(tm, p, q_tiles, bh, stream)
                       : launch_attn<2, 64, 3, 2, false>(tm, p, q_tiles, bh, stream);
     }
     switch (var) {
       case 1: return launch_attn<2, 64, 4, 3, true, true, 0x00, 0>(tm, p, q_tiles, bh, stream);
       case 2: return launch_attn<2, 64, 4, 3, true, true, 0x03, 0>(tm, p, q_tiles, bh, stream);
-      case 3: return launch_attn<2, 64, 4, 3, true, true, 0x11, 0>(tm, p, q_tiles, bh, stream);
-      case 4: return launch_attn<2, 64, 4, 3, true, true, 0x33, 0>(tm, p, q_tiles, bh, stream);
-      case 5: return launch_attn<2, 64, 4, 3, true, true, 0x0f, 0>(tm, p, q_tiles, bh, stream);
-      case 6: return launch_attn<2, 64, 4, 3, true, true, 0x13, 0>(tm, p, q_tiles, bh, stream);
-      case 7: return launch_attn<2, 64, 4, 3, true, true, 0x49, 0>(tm, p, q_tiles, bh, stream);
+      case 3: return launch_attn<2, 64, 4, 3, true, true, 0x00, 0, false, 2>(tm, p, q_tiles, bh, stream);
+      case 4: return launch_attn<2, 64, 4, 3, true, true, 0x03, 0, false, 2>(tm, p, q_tiles, bh, stream);
+      case 5: return launch_attn<2, 64, 4, 3, true, true, 0x13, 0, false, 2>(tm, p, q_tiles, bh, stream);
+      case 6: return launch_attn<2, 64, 4, 3, true, true, 0x33, 0, false, 2>(tm, p, q_tiles, bh, stream);
+      case 7: return launch_attn<2, 64, 4, 3, true, true, 0x11, 0, false, 2>(tm, p, q_tiles, bh, stream);
       default: return launch_attn<2, 64, 3, 2, true>(tm, p, q_tiles, bh, stream);
     }
   } else if (a->d_pad == 128) {
+    if (var >= 3)
+      return bf16 ? launch_attn<1, 128, 3, 2, true, true, 0, 0, false, 2>(tm, p, q_tiles, bh, stream)
+                  : launch_attn<1, 128, 3, 2, false, true, 0, 0, false, 2>(tm, p, q_tiles, bh, stream);
     if (var >= 1)
       return bf16 ? launch_attn<1, 128, 3, 2, true, true>(tm, p, q_tiles, bh, stream)
                   : launch_attn<1, 128, 3, 2, false, true>(tm, p, q_tiles, bh, stream);
     return bf16 ? launch_attn<1, 128, 2, 2, true>(tm, p, q_tiles, bh, stream)
                 : launch_attn<1, 128, 2, 2, false>(tm, p, q_tiles, bh, stream);
   } else {
+    if (var >= 3)
+      return bf16 ? launch_attn<1, 192, 2, 1, true, true, 0, 0, false, 2>(tm, p, q_tiles, bh, stream)
+                  : launch_attn<1, 192, 2, 1, false, true, 0, 0, false, 2>(tm, p, q_tiles, bh, stream);
     if (var >= 1)
       return bf16 ? launch_attn<1, 192, 2, 1, true, true>(tm, p, q_tiles, bh, stream)
                   : launch_attn<1, 192, 2, 1, false, true>(tm, p, q_tiles, bh, stream);
