@@ -273,3 +273,98 @@ class Generator(VidToMeGenerator):
     def unique_tensor_optimization(self):
         from .postopt import unique_tensor_optimization
         return unique_tensor_optimization(self)
+
+    # ---------------------------------------------------------------- pipeline level (generate.py:179-190, 552-630)
+    @torch.no_grad()
+    def encode_imgs_batch(self, imgs):
+        """generate_utils.py:157-172: frames [N,3,H,W] in [0,1] -> latents (posterior mean * 0.18215)."""
+        if self.vae is None:
+            raise TclError("Generator: pipe.vae is required (tclight_b200.vae.AutoencoderKLB200 or a diffusers VAE)")
+        if hasattr(self.vae, "encode_imgs"):
+            return self.vae.encode_imgs(imgs, batch_size=self.batch_size).to(self.dtype)
+        return torch.cat([self.vae.encode(2 * b.to(self.vae.dtype) - 1).latent_dist.mean * 0.18215
+                          for b in imgs.split(self.batch_size, dim=0)]).to(self.dtype)
+
+    @torch.no_grad()
+    def decode_latents_batch(self, latents):
+        """generate_utils.py:140-155: latents -> frames in [0,1]."""
+        if self.vae is None:
+            raise TclError("Generator: pipe.vae is required")
+        if hasattr(self.vae, "decode_latents"):
+            return self.vae.decode_latents(latents, batch_size=self.batch_size)
+        return torch.cat([(self.vae.decode(1 / 0.18215 * b.to(self.vae.dtype)).sample / 2 + 0.5).clamp(0, 1)
+                          for b in latents.split(self.batch_size, dim=0)])
+
+    @torch.no_grad()
+    def prepare_latents(self, n_frames: int, h: int, w: int):
+        """generate.py:179-190 (IC-Light branch): one noise map repeated for every frame (noise_mode "same") or
+        independent maps, scaled by the scheduler's init_noise_sigma; drawn from self.rng like
+        StableDiffusionPipeline.prepare_latents does."""
+        g = self.rng[0] if self.rng else None
+        dev = torch.device(self.device)
+        if self.noise_mode == "same":
+            x = torch.randn((1, 4, h, w), generator=g, device=g.device if g is not None else dev, dtype=torch.float32)
+            x = x.to(dev).repeat(n_frames, 1, 1, 1)
+        else:
+            x = torch.randn((n_frames, 4, h, w), generator=g, device=g.device if g is not None else dev, dtype=torch.float32).to(dev)
+        return (x * self.scheduler.init_noise_sigma).to(self.dtype)
+
+    @torch.no_grad()
+    def relight(self, frames, prompt_embeds, prompt_embeds_t, future_flows=None, past_flows=None, flow_alpha=0.5,
+                rgb_threshold=0.01):
+        """The device-resident core of ``Generator.__call__`` (generate.py:560-604) for one prompt, with everything
+        outside SURVEY §8 (CLIP text encoding, video decoding, the optical-flow network) supplied by the caller:
+
+            frames [N,3,H,W] in [0,1]; prompt_embeds / prompt_embeds_t = cat([uncond, cond]) [2,L,768];
+            future_flows / past_flows [N,2,H,W] (needed when post_opt.apply_opt)
+
+        VAE-encode the frames as the IC-Light condition -> multi-axis denoising -> VAE decode -> soft masks, flow ids,
+        unique inverse -> exposure alignment -> unique-video-tensor optimisation.  Returns (frames_out, info)."""
+        from . import flow_utils
+        from .postopt import OptDataset
+
+        N, _, H, W = frames.shape
+        self.scheduler.set_timesteps(self.n_timesteps, device=self.device)
+        if self.rng is None:
+            self.rng = [torch.Generator(device=self.device).manual_seed(int(self.seed))] * N
+        concat_conds = self.encode_imgs_batch(frames)
+        init_noise = self.prepare_latents(N, concat_conds.shape[2], concat_conds.shape[3])
+        clean_latent = self.ddim_sample(init_noise, prompt_embeds, prompt_embeds_t, concat_conds)
+        clean_frames = self.decode_latents_batch(clean_latent)
+        info = {"latent": clean_latent}
+        if self.apply_opt:
+            if future_flows is None or past_flows is None:
+                raise TclError("relight: post_opt.apply_opt needs future_flows and past_flows")
+            masks, unq_inv = flow_utils.build_unq_inv(frames.float(), future_flows.float(), past_flows.float(), alpha=flow_alpha,
+                                                      rgb_threshold=rgb_threshold)
+            if self.data_parser is None:
+                self.data_parser = type("DataParser", (), {})()
+            self.data_parser.unq_inv = unq_inv
+            self.dataset = OptDataset(clean_frames.float(), past_flows.float(), masks, device=self.device)
+            clean_frames, info["loss_exposure"] = self.exposure_align()
+            clean_frames, info["loss_unique_tensor"] = self.unique_tensor_optimization()
+            info["unq_inv"], info["mask_bwds"] = unq_inv, masks
+        return clean_frames, info
+
+    def __call__(self, latent_path, output_path, frame_ids):
+        """generate.py:560-630 with the B200 path.  Needs ``pipe.data_parser`` exposing ``load_video(frame_ids=...)`` and
+        ``load_flow(frame_ids, future_flow=True, past_flow=True, gts)`` like the reference's VideoDataParser, and a text
+        encoder (``self.encode_prompt_pair``) — both outside SURVEY §8 and not shipped here."""
+        dp = self.data_parser
+        if dp is None or not hasattr(dp, "load_video"):
+            raise TclError("Generator.__call__ needs pipe.data_parser (load_video / load_flow); use relight() with tensors")
+        if not hasattr(self, "encode_prompt_pair"):
+            raise TclError("Generator.__call__ needs a text encoder (encode_prompt_pair); use relight() with embeddings")
+        frames = dp.load_video(frame_ids=frame_ids)
+        frames = frames[0] if isinstance(frames, (tuple, list)) else frames
+        self.rng = [torch.Generator(device=self.device).manual_seed(int(self.seed))] * len(frame_ids)
+        flows = past = None
+        if self.apply_opt:
+            flows, past, _ = dp.load_flow(frame_ids, True, True, frames)
+        results = {}
+        for name, prompt in self.prompt.items():
+            c, u = self.encode_prompt_pair(prompt, self.negative_prompt)
+            ct, ut = self.encode_prompt_pair(self.prompt_t, self.negative_prompt_t)
+            results[name] = self.relight(frames.to(self.device), torch.cat([u, c]), torch.cat([ut, ct]), flows, past,
+                                         flow_alpha=getattr(dp, "alpha", 0.5))
+        return results
