@@ -39,8 +39,7 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, int c1, const void*
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
   if (sub < lanes) {
-    for (long long pix = p0 + sub; pix < p1; pix += lanes) {
-      const uint4 v = *reinterpret_cast<const uint4*>(src + ((long long)n * pix_per_img + pix) * cw + co);
+    auto acc = [&](const uint4& v) {
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -48,7 +47,18 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, int c1, const void*
         s[2 * j] += f.x; ss[2 * j] += f.x * f.x;
         s[2 * j + 1] += f.y; ss[2 * j + 1] += f.y * f.y;
       }
+    };
+    const typename E::T* base = src + (long long)n * pix_per_img * cw + co;
+    long long pix = p0 + sub;
+    // four independent 16-byte loads in flight per thread (the single-load loop was latency bound at ~1.5 TB/s)
+    for (; pix + 3LL * lanes < p1; pix += 4LL * lanes) {
+      const uint4 v0 = *reinterpret_cast<const uint4*>(base + pix * cw);
+      const uint4 v1 = *reinterpret_cast<const uint4*>(base + (pix + lanes) * cw);
+      const uint4 v2 = *reinterpret_cast<const uint4*>(base + (pix + 2LL * lanes) * cw);
+      const uint4 v3 = *reinterpret_cast<const uint4*>(base + (pix + 3LL * lanes) * cw);
+      acc(v0); acc(v1); acc(v2); acc(v3);
     }
+    for (; pix < p1; pix += lanes) acc(*reinterpret_cast<const uint4*>(base + pix * cw));
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       atomicAdd(&sh[ch + j], s[j]);
@@ -65,108 +75,123 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, int c1, const void*
   }
 }
 
+// y = x * a[c] + b[c] with a = rstd*gamma, b = beta - mean*rstd*gamma built once per block in shared memory
+// (blockIdx.y = image), so the streaming loop is one 16-byte load, 8 FMAs (+SiLU) and one 16-byte store per vector.
 template <bool BF16>
-__global__ void gn_apply_kernel(const void* __restrict__ x1, int c1, const void* __restrict__ x2, int c2,
-                                long long pix_per_img, int n_img, int groups, const float* __restrict__ stats,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                int silu, void* __restrict__ out) {
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const void* __restrict__ x1, int c1, const void* __restrict__ x2, int c2,
+                long long pix_per_img, int n_img, int groups, const float* __restrict__ stats,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                int silu, void* __restrict__ out) {
   using E = Elem<BF16>;
+  extern __shared__ float ab[];      // [2][C]
   const int C = c1 + c2;
   const int vecs = C / 8;
   const int cpg = C / groups;
+  const int n = blockIdx.y;
   const float inv_cnt = 1.0f / (float)(pix_per_img * cpg);
-  const long long total = (long long)n_img * pix_per_img * vecs;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sm = stats[((long long)n * groups + g) * 2 + 0];
+    const float sq = stats[((long long)n * groups + g) * 2 + 1];
+    const float mean = sm * inv_cnt;
+    const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+    const float a = rsqrtf(var + eps) * gamma[c];
+    ab[c] = a;
+    ab[C + c] = beta[c] - mean * a;
+  }
+  __syncthreads();
+  const long long total = pix_per_img * vecs;
+  const typename E::T* s1 = reinterpret_cast<const typename E::T*>(x1) + (long long)n * pix_per_img * c1;
+  const typename E::T* s2 = reinterpret_cast<const typename E::T*>(x2) + (long long)n * pix_per_img * c2;
+  typename E::T* dst = reinterpret_cast<typename E::T*>(out) + (long long)n * pix_per_img * C;
+  auto one = [&](long long i) {
     const int cb = (int)(i % vecs);
-    const long long pix = i / vecs;  // global pixel index (n*pix_per_img + p)
-    const int n = (int)(pix / pix_per_img);
+    const long long pix = i / vecs;
     const int ch = cb * 8;
-    const bool first = ch < c1;
-    const typename E::T* src = reinterpret_cast<const typename E::T*>(first ? x1 : x2);
-    const int cw = first ? c1 : c2;
-    const int co = first ? ch : ch - c1;
-    const uint4 v = *reinterpret_cast<const uint4*>(src + pix * cw + co);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    float f[8];
+    const uint4 v = ch < c1 ? *reinterpret_cast<const uint4*>(s1 + pix * c1 + ch)
+                            : *reinterpret_cast<const uint4*>(s2 + pix * c2 + (ch - c1));
+    const float4 a0 = *reinterpret_cast<const float4*>(ab + ch), a1 = *reinterpret_cast<const float4*>(ab + ch + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(ab + C + ch), b1 = *reinterpret_cast<const float4*>(ab + C + ch + 4);
+    const float2 f0 = E::unpack(v.x), f1 = E::unpack(v.y), f2 = E::unpack(v.z), f3 = E::unpack(v.w);
+    float y[8] = {fmaf(f0.x, a0.x, b0.x), fmaf(f0.y, a0.y, b0.y), fmaf(f1.x, a0.z, b0.z), fmaf(f1.y, a0.w, b0.w),
+                  fmaf(f2.x, a1.x, b1.x), fmaf(f2.y, a1.y, b1.y), fmaf(f3.x, a1.z, b1.z), fmaf(f3.y, a1.w, b1.w)};
+    if (silu) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 t = E::unpack(w[j]);
-      f[2 * j] = t.x; f[2 * j + 1] = t.y;
-    }
-    int g_prev = -1;
-    float mean = 0.f, rstd = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (ch + j) / cpg;
-      if (g != g_prev) {
-        const float sm = stats[((long long)n * groups + g) * 2 + 0];
-        const float sq = stats[((long long)n * groups + g) * 2 + 1];
-        mean = sm * inv_cnt;
-        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
-        rstd = rsqrtf(var + eps);
-        g_prev = g;
-      }
-      float y = (f[j] - mean) * rstd * gamma[ch + j] + beta[ch + j];
-      if (silu) y = silu_f(y);
-      f[j] = y;
+      for (int j = 0; j < 8; ++j) y[j] = silu_f(y[j]);
     }
     uint4 o;
-    o.x = E::pack(f[0], f[1]); o.y = E::pack(f[2], f[3]); o.z = E::pack(f[4], f[5]); o.w = E::pack(f[6], f[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<typename E::T*>(out) + pix * C + ch) = o;
-  }
+    o.x = E::pack(y[0], y[1]); o.y = E::pack(y[2], y[3]); o.z = E::pack(y[4], y[5]); o.w = E::pack(y[6], y[7]);
+    *reinterpret_cast<uint4*>(dst + pix * C + ch) = o;
+  };
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i + stride < total; i += 2 * stride) { one(i); one(i + stride); }
+  if (i < total) one(i);
 }
 
 // ------------------------------------------------------------------------------------------
 // LayerNorm over the last dim (C <= 2048, C % 8 == 0): one warp per row, two-pass in registers.
 // ------------------------------------------------------------------------------------------
-template <bool BF16>
-__global__ void layernorm_kernel(const void* __restrict__ x, long long rows, int C, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, float eps, void* __restrict__ out) {
+// LPR lanes share one row (8 / 16 / 32: the smallest that keeps <= VPL vectors of 8 per lane), so a warp normalises
+// 32/LPR rows at once with every lane busy; all of a lane's 16-byte loads are issued before the first use.
+template <bool BF16, int LPR, int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const void* __restrict__ x, long long rows, int C, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, void* __restrict__ out) {
   using E = Elem<BF16>;
-  const int warps_per_block = blockDim.x >> 5;
-  const long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  constexpr int RPW = 32 / LPR;                     // rows per warp
   const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+  const bool live = row < rows;
   const int vecs = C / 8;
-  constexpr int MAXV = 8;  // up to 8 vectors of 8 per lane => C <= 2048
-  float f[MAXV][8];
-  const typename E::T* src = reinterpret_cast<const typename E::T*>(x) + row * C;
+  const typename E::T* src = reinterpret_cast<const typename E::T*>(x) + (live ? row : 0) * C;
+  uint4 raw[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v = l + k * LPR;
+    raw[k] = (live && v < vecs) ? *reinterpret_cast<const uint4*>(src + v * 8) : make_uint4(0, 0, 0, 0);
+  }
+  float f[VPL][8];
   float sum = 0.f;
 #pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    const int v = lane + k * 32;
-    if (v < vecs) {
-      const uint4 u = *reinterpret_cast<const uint4*>(src + v * 8);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int k = 0; k < VPL; ++k) {
+    const uint32_t w[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 t = E::unpack(w[j]);
-        f[k][2 * j] = t.x; f[k][2 * j + 1] = t.y;
-        sum += t.x + t.y;
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = E::unpack(w[j]);
+      f[k][2 * j] = t.x; f[k][2 * j + 1] = t.y;
+      sum += t.x + t.y;
     }
   }
-  sum = warp_sum(sum);
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / (float)C;
   float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    const int v = lane + k * 32;
-    if (v < vecs) {
+  for (int k = 0; k < VPL; ++k) {
+    if (l + k * LPR < vecs) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { const float dlt = f[k][j] - mean; sq += dlt * dlt; }
     }
   }
-  sq = warp_sum(sq);
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq / (float)C + eps);
+  if (!live) return;
   typename E::T* dst = reinterpret_cast<typename E::T*>(out) + row * C;
 #pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    const int v = lane + k * 32;
+  for (int k = 0; k < VPL; ++k) {
+    const int v = l + k * LPR;
     if (v < vecs) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float y[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = (f[k][j] - mean) * rstd * gamma[v * 8 + j] + beta[v * 8 + j];
+      for (int j = 0; j < 8; ++j) y[j] = (f[k][j] - mean) * rstd * gg[j] + bb[j];
       uint4 o;
       o.x = E::pack(y[0], y[1]); o.y = E::pack(y[2], y[3]); o.z = E::pack(y[4], y[5]); o.w = E::pack(y[6], y[7]);
       *reinterpret_cast<uint4*>(dst + v * 8) = o;
@@ -323,9 +348,14 @@ extern "C" int tcl_groupnorm(int dtype, const void* x1, int c1, const void* x2, 
   if (bf) gn_stats_kernel<true><<<grid, block, sh, stream>>>(x1, c1, x2, c2, pix_per_img, groups, stats_ws, (int)ppb);
   else gn_stats_kernel<false><<<grid, block, sh, stream>>>(x1, c1, x2, c2, pix_per_img, groups, stats_ws, (int)ppb);
   TCL_CHECK_LAUNCH("tcl_groupnorm(stats)");
-  const long long total = (long long)n_img * pix_per_img * vecs;
-  if (bf) gn_apply_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(x1, c1, x2, c2, pix_per_img, n_img, groups, stats_ws, gamma, beta, eps, silu, out);
-  else gn_apply_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(x1, c1, x2, c2, pix_per_img, n_img, groups, stats_ws, gamma, beta, eps, silu, out);
+  const long long total = pix_per_img * vecs;                 // vectors per image
+  long long ax = (total + 511) / 512;                         // two vectors per thread per trip
+  const long long cap = (148LL * 16 + n_img - 1) / n_img;
+  if (ax > cap) ax = cap;
+  if (ax < 1) ax = 1;
+  const dim3 agrid((unsigned)ax, (unsigned)n_img);
+  if (bf) gn_apply_kernel<true><<<agrid, 256, sh, stream>>>(x1, c1, x2, c2, pix_per_img, n_img, groups, stats_ws, gamma, beta, eps, silu, out);
+  else gn_apply_kernel<false><<<agrid, 256, sh, stream>>>(x1, c1, x2, c2, pix_per_img, n_img, groups, stats_ws, gamma, beta, eps, silu, out);
   TCL_CHECK_LAUNCH("tcl_groupnorm(apply)");
   return TCL_OK;
 }
@@ -335,10 +365,24 @@ extern "C" int tcl_layernorm(int dtype, const void* x, long long rows, int C, co
   TCL_CHECK_ARG(x && out && gamma && beta, "tcl_layernorm: null pointer");
   TCL_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 2048, "tcl_layernorm: C=%d", C);
   if (rows <= 0) return TCL_OK;
+  TCL_CHECK_ARG(((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "tcl_layernorm: gamma/beta must be 16-byte aligned");
   const int wpb = 8;
-  const long long blocks = (rows + wpb - 1) / wpb;
-  if (dtype == TCL_DTYPE_BF16) layernorm_kernel<true><<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, gamma, beta, eps, out);
-  else layernorm_kernel<false><<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, gamma, beta, eps, out);
+  const int vecs = C / 8;
+  const bool bf = dtype == TCL_DTYPE_BF16;
+#define TCL_LN(LPR, VPL)                                                                                               \
+  do {                                                                                                                 \
+    const long long rpb = (long long)wpb * (32 / LPR);                                                                 \
+    const long long blocks = (rows + rpb - 1) / rpb;                                                                   \
+    if (bf) layernorm_kernel<true, LPR, VPL><<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, gamma, beta, eps, out);  \
+    else layernorm_kernel<false, LPR, VPL><<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, gamma, beta, eps, out);    \
+  } while (0)
+  if (vecs <= 8) TCL_LN(8, 1);            // C <= 64
+  else if (vecs <= 16) TCL_LN(8, 2);      // C <= 128
+  else if (vecs <= 40) TCL_LN(8, 5);      // C <= 320
+  else if (vecs <= 80) TCL_LN(16, 5);     // C <= 640
+  else if (vecs <= 160) TCL_LN(32, 5);    // C <= 1280
+  else TCL_LN(32, 8);                     // C <= 2048
+#undef TCL_LN
   TCL_CHECK_LAUNCH("tcl_layernorm");
   return TCL_OK;
 }
