@@ -113,6 +113,7 @@ class VidToMeGenerator(nn.Module):
         return None  # only PnP does work here (generate_utils.py:228-233)
 
     def post_iter(self, x, t):
+        vidtome.assert_draws_consumed(self.pipe)
         if self.merge_global:
             vidtome.update_patch(self.pipe, global_tokens=None)   # generate_utils.py:235-238
 
@@ -171,7 +172,9 @@ class Generator(VidToMeGenerator):
         f0, f1 = self._my_range(len(x))
         if sharded:
             noises.zero_()
-        for chunk in self.get_chunks(f1 - f0):
+        chunks = self.get_chunks(f1 - f0)
+        vidtome.prefetch_draws(self.pipe, [len(c) for c in chunks])     # one host sync for the pass instead of one per block
+        for chunk in chunks:
             lo, hi = _as_range(chunk)
             lo, hi = lo + f0, hi + f0
             cc = concat_conds[lo:hi] if concat_conds is not None else None
@@ -232,6 +235,7 @@ class Generator(VidToMeGenerator):
         if sharded:
             noises_t.zero_()
         chunks = self.get_chunks(w1 - w0)
+        vidtome.prefetch_draws(self.pipe, [len(c) for _ in sl_idxs for c in chunks])
         for idx, sl_i in enumerate(sl_idxs):
             for chunk in chunks:
                 c0, c1 = _as_range(chunk)

@@ -19,6 +19,8 @@ from typing import Any, Callable, Dict, Tuple
 
 import torch
 
+from .._lib import TclError
+
 from . import merge
 from .utils import func_warper, init_generator, isinstance_str, join_frame, join_warper, split_warper
 from .. import ops
@@ -45,7 +47,9 @@ def compute_merge_plan(module, x: torch.Tensor, tome_info: Dict[str, Any]):
     tsize = x.shape[1]
 
     if downsample > args["max_downsample"]:
+        module._tome_active = False
         return merge.do_nothing, merge.do_nothing, x, None
+    module._tome_active = True
 
     if args["generator"] is None:
         args["generator"] = init_generator(x.device)
@@ -55,17 +59,30 @@ def compute_merge_plan(module, x: torch.Tensor, tome_info: Dict[str, Any]):
     do_local = fsize > 1 and args["local_merge_ratio"] > 0
     has_pool = args["merge_global"] and getattr(module, "global_tokens", None) is not None
     # ---- random draws, reference order: randint inside randframe (merge.py:57), then rand (patch.py:62)
-    draws = []
-    if do_local:
-        draws.append(torch.randint(0, min(args["target_stride"], fsize), torch.Size([1]), generator=generator,
-                                   device=generator.device).to(torch.float32))
-    elif fsize > 1:
-        pass
-    if has_pool:
-        draws.append(torch.rand(1, generator=generator, device=generator.device))
-    vals = torch.cat(draws).tolist() if draws else []
-    randf = int(vals[0]) if do_local else None
-    grand = vals[-1] if has_pool else None
+    queue = getattr(module, "_draw_queue", None)
+    if queue:
+        # values drawn ahead of time by prefetch_draws (same generator, same call order, ONE host sync per pass)
+        randf = grand = None
+        if do_local:
+            kind, bound, val = queue.popleft()
+            if kind != "i" or bound != min(args["target_stride"], fsize):
+                raise TclError("VidToMe draw queue out of step with the chunk plan (local draw)")
+            randf = int(val)
+        if has_pool:
+            kind, _, val = queue.popleft()
+            if kind != "r":
+                raise TclError("VidToMe draw queue out of step with the chunk plan (global draw)")
+            grand = val
+    else:
+        draws = []
+        if do_local:
+            draws.append(torch.randint(0, min(args["target_stride"], fsize), torch.Size([1]), generator=generator,
+                                       device=generator.device).to(torch.float32))
+        if has_pool:
+            draws.append(torch.rand(1, generator=generator, device=generator.device))
+        vals = torch.cat(draws).tolist() if draws else []          # host sync: the roles decide tensor shapes
+        randf = int(vals[0]) if do_local else None
+        grand = vals[-1] if has_pool else None
 
     local_tokens = join_frame(x, fsize)
     m_ls = [join_warper(fsize)]
@@ -165,6 +182,61 @@ def apply_patch(model, local_merge_ratio: float = 0.9, merge_global: bool = Fals
             module._tome_info = unet._tome_info
             module._tome_patched = True
     return model
+
+
+def prefetch_draws(model, fsizes) -> int:
+    """Draws, ahead of time, every random number the patched blocks will consume during a pass whose chunk-forwards
+    have ``fsizes`` frames each (reference order per module generator: ``randint`` for the target frame when the
+    chunk is merged locally, merge.py:57, then ``rand`` for the global-merge role when a pool exists, patch.py:62),
+    and fetches them with ONE device->host copy.  Without this every block of every chunk-forward synchronises the
+    host (2 750 times per 300-frame step), which leaves the GPU idle while Python refills the launch queue.  The
+    generators see exactly the same calls in the same order, so the values — and therefore the merge indices — are
+    unchanged.  Blocks that have not run yet (no generator forked, activity unknown) keep drawing directly.
+    Returns the number of values prefetched."""
+    import collections
+
+    unet = _unet_of(model)
+    info = getattr(unet, "_tome_info", None)
+    if info is None:
+        return 0
+    args = info["args"]
+    todo = []
+    for _, module in unet.named_modules():
+        if not getattr(module, "_tome_patched", False) or not getattr(module, "_tome_active", False):
+            continue
+        gen = getattr(module, "generator", None)
+        if gen is None:
+            continue
+        if getattr(module, "_draw_queue", None):
+            raise TclError("VidToMe draw queue not empty at the start of a pass")
+        has_pool = bool(args["merge_global"]) and getattr(module, "global_tokens", None) is not None
+        q = []
+        for fs in fsizes:
+            if fs > 1 and args["local_merge_ratio"] > 0:
+                bound = min(args["target_stride"], fs)
+                q.append(["i", bound, torch.randint(0, bound, torch.Size([1]), generator=gen, device=gen.device).to(torch.float32)])
+            if has_pool:
+                q.append(["r", 0, torch.rand(1, generator=gen, device=gen.device)])
+            if args["merge_global"]:
+                has_pool = True
+        module._draw_queue = q
+        todo += q
+    if todo:
+        vals = torch.cat([t[2].reshape(1) for t in todo]).tolist()
+        for t, v in zip(todo, vals):
+            t[2] = v
+    for _, module in unet.named_modules():
+        q = getattr(module, "_draw_queue", None)
+        if isinstance(q, list):
+            module._draw_queue = collections.deque(q)
+    return len(todo)
+
+
+def assert_draws_consumed(model) -> None:
+    unet = _unet_of(model)
+    for name, module in unet.named_modules():
+        if getattr(module, "_draw_queue", None):
+            raise TclError(f"VidToMe draw queue of {name} has {len(module._draw_queue)} unconsumed values")
 
 
 def remove_patch(model):

@@ -195,3 +195,46 @@ def test_vae_oracle_shapes():
     assert z.shape == (1, 4, 5, 7)
     y = V.decode_latents(m, z)
     assert y.shape == x.shape and 0 <= float(y.min()) and float(y.max()) <= 1
+
+
+def test_prefetch_draws_equals_sequential_draws():
+    """vidtome.prefetch_draws consumes each block generator with the reference's calls in the reference's order
+    (randint for the target frame when a chunk has > 1 frame, then rand for the global role once a pool exists), so the
+    prefetched values are the ones the per-call draws would have produced."""
+    import pytest
+    import torch
+    from tclight_b200._lib import TclError
+    from tclight_b200.vidtome import patch
+
+    args = dict(merge_global=True, local_merge_ratio=0.6, target_stride=4, global_rand=0.5, max_downsample=2)
+    unet = torch.nn.Module()
+    unet._tome_info = {"size": None, "args": args}
+    blocks = []
+    for k in range(3):
+        b = torch.nn.Module()
+        b._tome_info, b._tome_patched, b._tome_active = unet._tome_info, True, k != 2   # block 2: level skipped (ds > 2)
+        b.generator = torch.Generator().manual_seed(100 + k)
+        b.global_tokens = None if k == 0 else torch.zeros(1)                             # block 1 already has a pool
+        setattr(unet, f"b{k}", b)
+        blocks.append(b)
+    fsizes = [3, 4, 4, 1, 4, 2]
+    n = patch.prefetch_draws(unet, fsizes)
+    assert not getattr(blocks[2], "_draw_queue", None)
+    total = 0
+    for k in (0, 1):
+        ref = torch.Generator().manual_seed(100 + k)
+        has_pool = k == 1
+        want = []
+        for fs in fsizes:
+            if fs > 1:
+                want.append(["i", min(4, fs), float(torch.randint(0, min(4, fs), (1,), generator=ref))])
+            if has_pool:
+                want.append(["r", 0, float(torch.rand(1, generator=ref))])
+            has_pool = True
+        assert [list(e) for e in blocks[k]._draw_queue] == want
+        total += len(want)
+    assert n == total
+    with pytest.raises(TclError):
+        patch.assert_draws_consumed(unet)
+    with pytest.raises(TclError):
+        patch.prefetch_draws(unet, [4])          # a pass must start with empty queues

@@ -19,7 +19,8 @@ def _fake_pred(self, x, cond, t, concat_conds=None, batch_idx=None, sl_i=None, o
 def _make(rank, world):
     from tclight_b200.generate import Generator
 
-    g = types.SimpleNamespace(chunk_size=4, merge_global=True, chunk_ord="mix", perm_div=4.0, win_size_t=6, guidance_scale=2.0)
+    g = types.SimpleNamespace(chunk_size=4, merge_global=True, chunk_ord="mix", perm_div=4.0, win_size_t=6, guidance_scale=2.0,
+                              pipe=types.SimpleNamespace(unet=torch.nn.Identity()))     # un-patched stand-in: no VidToMe draws to prefetch
     for name in ("get_chunks", "_my_range", "_allreduce", "set_shard", "xy_pass", "yt_pass"):
         setattr(g, name, types.MethodType(getattr(Generator, name), g))
     g.temporal_windows = Generator.temporal_windows
