@@ -108,8 +108,8 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 // SPLIT: softmax warpgroups per Q tile.  With 2, each thread owns one row x 64 score columns and the two halves
 //        exchange their row maxima through shared memory: 4 softmax warps per scheduler instead of 2 keep the XU
 //        pipe (MUFU.EX2 + F2FP, the binding pipe) busy while other warps sit in their load / max / store phases.
-template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS, int POLY, int STAG, bool IPACK, int SPLIT>
-__global__ void __launch_bounds__(NQ * 128 * SPLIT + 32 + NQ * 32, 1)
+template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS, int POLY, int STAG, bool IPACK, int SPLIT, int MINB>
+__global__ void __launch_bounds__(NQ * 128 * SPLIT + 32 + NQ * 32, MINB)
 attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnParams p) {
   using E = Elem<BF16>;
   constexpr int NC = DPAD / 64;                    // 64-wide chunks of the head dim
@@ -472,13 +472,14 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
   }
 }
 
-template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS = false, int POLY = 0, int STAG = 0, bool IPACK = false, int SPLIT = 1>
+template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS = false, int POLY = 0, int STAG = 0, bool IPACK = false, int SPLIT = 1,
+          int MINB = 1>
 static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, int bh, cudaStream_t stream) {
   constexpr size_t smem = (size_t)NQ * 128 * DPAD * 2 + (size_t)KST * 128 * DPAD * 2 +
                           (size_t)VST * 2 * DPAD * 128 + (TS ? 0 : (size_t)NQ * 128 * 128 * 2) + 1024 + 256 + 4096;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG, IPACK, SPLIT>,
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG, IPACK, SPLIT, MINB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_last_error("attention: cudaFuncSetAttribute(%zu B) failed: %s", smem, cudaGetErrorString(e));
@@ -487,7 +488,7 @@ static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, in
     configured = true;
   }
   dim3 grid((q_tiles + NQ - 1) / NQ, bh);
-  attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG, IPACK, SPLIT><<<grid, NQ * 128 * SPLIT + 32 + NQ * 32, smem, stream>>>(tm, p);
+  attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG, IPACK, SPLIT, MINB><<<grid, NQ * 128 * SPLIT + 32 + NQ * 32, smem, stream>>>(tm, p);
   TCL_CHECK_LAUNCH("tcl_attention");
   return TCL_OK;
 }
@@ -544,6 +545,13 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
   const int q_tiles = (a->tq + 127) / 128;
   const int var = g_attn_variant;
   if (a->d_pad == 64) {
+    // short key sequences (cross-attention on the 77 / 154 text tokens): the per-CTA latency chain (TMEM alloc, Q / K / V
+    // loads, two serial tiles, epilogue) dominates, so run one Q tile per CTA and two CTAs per SM (256 TMEM columns,
+    // 85 KB of shared memory each) to overlap the chains of neighbouring tiles
+    if (var >= 1 && var != 8 && a->tk <= 256) {
+      return bf16 ? launch_attn<1, 64, 2, 2, true, true, 0x03, 0, false, 1, 2>(tm, p, q_tiles, bh, stream)
+                  : launch_attn<1, 64, 2, 2, false, true, 0x00, 0, false, 1, 2>(tm, p, q_tiles, bh, stream);
+    }
     if (!bf16) {
       if (var >= 3) return launch_attn<2, 64, 4, 3, false, true, 0, 0, false, 2>(tm, p, q_tiles, bh, stream);
       return var >= 1 ? launch_attn<2, 64, 4, 3, false, true>(tm, p, q_tiles, bh, stream)
@@ -551,7 +559,7 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
     }
     switch (var) {
       case 1: return launch_attn<2, 64, 4, 3, true, true, 0x00, 0>(tm, p, q_tiles, bh, stream);
-      case 2: return launch_attn<2, 64, 4, 3, true, true, 0x03, 0>(tm, p, q_tiles, bh, stream);
+      case 2: case 8: return launch_attn<2, 64, 4, 3, true, true, 0x03, 0>(tm, p, q_tiles, bh, stream);
       case 3: return launch_attn<2, 64, 4, 3, true, true, 0x00, 0, false, 2>(tm, p, q_tiles, bh, stream);
       case 4: return launch_attn<2, 64, 4, 3, true, true, 0x03, 0, false, 2>(tm, p, q_tiles, bh, stream);
       case 5: return launch_attn<2, 64, 4, 3, true, true, 0x13, 0, false, 2>(tm, p, q_tiles, bh, stream);
