@@ -106,3 +106,69 @@ def random_state_dict(seed: int = 0, block_out_channels=(320, 640, 1280, 1280), 
     norm("conv_norm_out", boc[0])
     conv("conv_out", out_channels, boc[0], 3)
     return sd
+
+
+def random_vae_state_dict(seed: int = 0, block_out_channels=(128, 256, 512, 512), latent_channels: int = 4,
+                          in_channels: int = 3, out_channels: int = 3):
+    """Seeded random weights with diffusers' SD-1.5 ``AutoencoderKL`` state-dict keys and shapes (what
+    ``pipe.vae.state_dict()`` returns; a real checkpoint loads through the same keys)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def lin(name, o, i):
+        b = 1.0 / (i ** 0.5)
+        sd[name + ".weight"] = (torch.rand(o, i, generator=g) * 2 - 1) * b
+        sd[name + ".bias"] = (torch.rand(o, generator=g) * 2 - 1) * b
+
+    def conv(name, o, i, k):
+        b = 1.0 / ((i * k * k) ** 0.5)
+        sd[name + ".weight"] = (torch.rand(o, i, k, k, generator=g) * 2 - 1) * b
+        sd[name + ".bias"] = (torch.rand(o, generator=g) * 2 - 1) * b
+
+    def norm(name, c):
+        sd[name + ".weight"] = torch.ones(c)
+        sd[name + ".bias"] = torch.zeros(c)
+
+    def resnet(p, ci, co):
+        norm(p + "norm1", ci)
+        conv(p + "conv1", co, ci, 3)
+        norm(p + "norm2", co)
+        conv(p + "conv2", co, co, 3)
+        if ci != co:
+            conv(p + "conv_shortcut", co, ci, 1)
+
+    def mid(p, c):
+        resnet(p + "resnets.0.", c, c)
+        a = p + "attentions.0."
+        norm(a + "group_norm", c)
+        for n in ("to_q", "to_k", "to_v", "to_out.0"):
+            lin(a + n, c, c)
+        resnet(p + "resnets.1.", c, c)
+
+    boc = tuple(block_out_channels)
+    conv("encoder.conv_in", boc[0], in_channels, 3)
+    c = boc[0]
+    for i, co in enumerate(boc):
+        resnet(f"encoder.down_blocks.{i}.resnets.0.", c, co)
+        resnet(f"encoder.down_blocks.{i}.resnets.1.", co, co)
+        if i < len(boc) - 1:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", co, co, 3)
+        c = co
+    mid("encoder.mid_block.", c)
+    norm("encoder.conv_norm_out", c)
+    conv("encoder.conv_out", 2 * latent_channels, c, 3)
+    conv("quant_conv", 2 * latent_channels, 2 * latent_channels, 1)
+    conv("post_quant_conv", latent_channels, latent_channels, 1)
+    rev = list(reversed(boc))
+    conv("decoder.conv_in", rev[0], latent_channels, 3)
+    mid("decoder.mid_block.", rev[0])
+    c = rev[0]
+    for i, co in enumerate(rev):
+        for j in range(3):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}.", c if j == 0 else co, co)
+        if i < len(rev) - 1:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", co, co, 3)
+        c = co
+    norm("decoder.conv_norm_out", c)
+    conv("decoder.conv_out", out_channels, c, 3)
+    return sd

@@ -238,3 +238,14 @@ def test_prefetch_draws_equals_sequential_draws():
         patch.assert_draws_consumed(unet)
     with pytest.raises(TclError):
         patch.prefetch_draws(unet, [4])          # a pass must start with empty queues
+
+
+def test_random_vae_state_dict_has_diffusers_keys():
+    from oracle import vae_ref as V
+    from tclight_b200.weights import random_vae_state_dict
+
+    for boc in [(128, 256, 512, 512), (64, 64, 128, 128)]:
+        sd = random_vae_state_dict(seed=1, block_out_channels=boc)
+        ref = V.make_vae(block_out_channels=boc)
+        assert set(sd) == set(ref.state_dict()) and all(sd[k].shape == v.shape for k, v in ref.state_dict().items())
+        ref.load_state_dict(sd)

@@ -2,11 +2,11 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import vae_ref as V        # only used to create a diffusers-keyed random state dict
 from tclight_b200.vae import AutoencoderKLB200
+from tclight_b200.weights import random_vae_state_dict
 
 dev = torch.device("cuda")
-sd = V.make_vae(seed=0).state_dict()
+sd = random_vae_state_dict(seed=0)
 vae = AutoencoderKLB200(sd, device=dev, dtype=torch.bfloat16)
 lat = (0.18215 * torch.randn(4, 4, 90, 160, device=dev)).to(torch.bfloat16)
 img = torch.rand(4, 3, 720, 1280, device=dev)
