@@ -1,4 +1,5 @@
-"""2-GPU check of the data-parallel optimiser: run under torchrun with 2 ranks; every rank runs the DP
+"""2-GPU parity check of the data-parallel optimiser (not collected by pytest; run on a 2-GPU box:
+`python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dp_postopt_check_2gpu.py`); every rank runs the DP
 path, rank 0 also runs the single-GPU path and the oracle and compares losses / images."""
 import os, sys, types
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
