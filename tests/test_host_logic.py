@@ -249,3 +249,78 @@ def test_random_vae_state_dict_has_diffusers_keys():
         ref = V.make_vae(block_out_channels=boc)
         assert set(sd) == set(ref.state_dict()) and all(sd[k].shape == v.shape for k, v in ref.state_dict().items())
         ref.load_state_dict(sd)
+
+
+def test_video_dataparser_host_side(tmp_path):
+    """Frame decoding / resizing / flow-cache layout of tclight_b200.dataparser (CPU-only parts)."""
+    import cv2
+    import numpy as np
+    import pytest
+    import torch
+    import types
+    from tclight_b200 import dataparser as D
+    from tclight_b200._lib import TclError
+
+    rng = np.random.default_rng(0)
+    vdir = tmp_path / "clip"
+    vdir.mkdir()
+    raw = rng.integers(0, 255, size=(5, 40, 72, 3), dtype=np.uint8)
+    for i, im in enumerate(raw):
+        cv2.imwrite(str(vdir / f"{i:04d}.png"), cv2.cvtColor(im, cv2.COLOR_RGB2BGR))
+    cfg = types.SimpleNamespace(rgb_path=str(vdir), height=32, width=48, fps=25)
+    dp = D.VideoDataParser(cfg, device="cpu")
+    assert dp.n_frames == 5 and dp.alpha == 0.5 and dp.flow_model == "memflow"
+    rgbs = dp.load_video(frame_ids=[0, 2, 4])
+    assert rgbs.shape == (3, 3, 32, 48) and 0 <= float(rgbs.min()) and float(rgbs.max()) <= 1
+    # resize-to-cover + centre crop: 40x72 -> scale max(48/72, 32/40) = 0.8 -> 32x58 -> crop 32x48
+    full = torch.from_numpy(raw[[0, 2, 4]]).permute(0, 3, 1, 2).float() / 255
+    assert torch.equal(rgbs, D.process_frames(full, 32, 48))
+    assert D.get_frame_ids([0, -1], 5) == [0, 1, 2, 3, 4] and D.get_frame_ids([1, 9], 5) == [1, 2, 3, 4]
+    assert D.get_frame_ids([0, 3], 5, frame_ids=[4, 1]) == [1, 4]
+    # flow cache layout of the reference: <frame dir>/future_flow_memflow/<id:04d>.pt, tensors [1,2,h,w] (the reference
+    # estimates flows on the processed frames)
+    fdir = vdir / "future_flow_memflow"
+    fdir.mkdir()
+    for i in (0, 2, 4):
+        torch.save(torch.full((1, 2, 32, 48), float(i)), str(fdir / f"{i:04d}.pt"))
+    flows, pasts, masks = dp.load_flow([0, 2, 4], future_flow=True, past_flow=False, gts=rgbs, save_flow=False)
+    assert pasts is None and masks is None and flows.shape == (3, 2, 32, 48)
+    assert torch.allclose(flows[1], torch.full((2, 32, 48), 2.0))
+    # flows stored at another resolution are resized like the frames and their vectors scaled by the resize factor
+    assert torch.allclose(dp.process_flow([torch.full((2, 40, 72), 5.0)]), torch.full((1, 2, 32, 48), 5.0 * 0.8))
+    # a missing flow without a flow_fn is an error, not a silent zero
+    (fdir / "0002.pt").unlink()
+    with pytest.raises(TclError):
+        dp.load_flow([0, 2, 4], future_flow=True, past_flow=False, gts=rgbs, save_flow=False)
+    # ... and is produced (and cached) by a caller-supplied estimator
+    dp.flow_fn = lambda s, t: torch.ones(1, 2, s.shape[-2], s.shape[-1])
+    flows, _, _ = dp.load_flow([0, 2, 4], future_flow=True, past_flow=False, gts=rgbs, save_flow=True)
+    assert (fdir / "0002.pt").exists() and torch.allclose(flows[1], torch.ones(2, 32, 48))
+
+
+def test_process_frames_matches_reference():
+    import pytest
+    import torch
+    from oracle import refshim
+
+    if not refshim.reference_available():
+        pytest.skip("reference tree not mounted")
+    import importlib
+    import os
+
+    from tclight_b200 import dataparser as D
+
+    refshim.install()
+    cwd = os.getcwd()
+    os.chdir(refshim.REF_ROOT)
+    try:
+        ru = importlib.import_module("utils.VidToMe.utils")
+        rg = importlib.import_module("utils.general_utils")
+    finally:
+        os.chdir(cwd)
+    g = torch.Generator().manual_seed(0)
+    fr = torch.rand(3, 3, 50, 90, generator=g)
+    assert torch.equal(D.process_frames(fr, 32, 48), ru.process_frames(fr, 32, 48, 8))
+    fl = torch.randn(3, 2, 50, 90, generator=g)
+    assert torch.equal(D.process_frames(fl, 40, 64), rg.process_frames(fl, 40, 64))
+    assert D.get_frame_ids([0, -1], 7) == ru.get_frame_ids([0, -1], 7)
