@@ -324,3 +324,38 @@ def test_process_frames_matches_reference():
     fl = torch.randn(3, 2, 50, 90, generator=g)
     assert torch.equal(D.process_frames(fl, 40, 64), rg.process_frames(fl, 40, 64))
     assert D.get_frame_ids([0, -1], 7) == ru.get_frame_ids([0, -1], 7)
+
+
+def test_iclight_weight_surgery_matches_reference_recipe():
+    """iclight_merge_state_dict == the reference's conv_in widening + offset addition (utils/model_utils.py:22-26, 50-54)."""
+    import pytest
+    import torch
+    from tclight_b200._lib import TclError
+    from tclight_b200.model_utils import iclight_merge_state_dict
+
+    g = torch.Generator().manual_seed(0)
+    origin = {"conv_in.weight": torch.randn(6, 4, 3, 3, generator=g), "conv_in.bias": torch.randn(6, generator=g),
+              "mid.weight": torch.randn(5, 5, generator=g)}
+    # the reference: new Conv2d(8, ...) with zero weight, copy the first 4 input channels, keep the bias; then add offsets
+    conv = torch.nn.Conv2d(8, 6, 3, 1, 1)
+    with torch.no_grad():
+        conv.weight.zero_()
+        conv.weight[:, :4].copy_(origin["conv_in.weight"])
+    ref_origin = {"conv_in.weight": conv.weight.detach(), "conv_in.bias": origin["conv_in.bias"], "mid.weight": origin["mid.weight"]}
+    offset = {k: torch.randn(v.shape, generator=g) for k, v in ref_origin.items()}
+    want = {k: ref_origin[k] + offset[k] for k in ref_origin}
+    got = iclight_merge_state_dict(origin, offset)
+    assert set(got) == set(want) and all(torch.equal(got[k], want[k]) for k in want)
+    assert got["conv_in.weight"].shape == (6, 8, 3, 3) and torch.equal(got["conv_in.weight"][:, 4:], offset["conv_in.weight"][:, 4:])
+    with pytest.raises(TclError):
+        iclight_merge_state_dict(origin, {k: v for k, v in offset.items() if k != "mid.weight"})
+
+
+def test_run_cli_requires_cuda_for_synthetic(capsys):
+    import torch
+    from tclight_b200 import run
+
+    if torch.cuda.is_available():
+        return
+    assert run.main(["--synthetic", "--small"]) == 2
+    assert "CUDA device is required" in capsys.readouterr().err
