@@ -48,6 +48,8 @@ def run_synthetic(a) -> int:
     cfg = default_config(n_timesteps=a.steps, alpha_t=0.01)
     cfg.float_precision = "bf16"
     cfg.post_opt.epochs_exposure, cfg.post_opt.epochs = a.opt_epochs, a.opt_epochs
+    # the reference's lr schedule spans epochs * N // batch iterations (generate.py:385): keep it >= 1 on short clips
+    cfg.post_opt.batch_size = max(1, min(int(cfg.post_opt.batch_size), a.frames))
     seed_everything(cfg.seed)
     small = a.small
     pipe, scheduler, cfg.model_key = init_synthetic(
