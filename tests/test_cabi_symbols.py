@@ -61,3 +61,38 @@ def test_product_never_imports_oracle():
                     if "smoke_check" not in fn:
                         offenders.append((f, m.group(0).strip()))
     assert not offenders, offenders
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Argument checks of the producer / VAE / DDIM entry points run on the host before any CUDA call."""
+    import ctypes as C
+    from tclight_b200 import _lib
+
+    lib = _lib.lib
+    one = C.c_void_p(16)           # non-null, 16-byte aligned dummy pointer (never dereferenced: the checks fail first)
+    # N*H*W >= 2^31 needs int64 ids: refused
+    assert lib.tcl_flow_ids(one, one, one, 4096, 1024, 1024, 0.01, one, one, None, one, 1 << 40, None) != 0
+    assert b"int64" in lib.tcl_last_error()
+    # workspace too small
+    assert lib.tcl_flow_ids(one, one, one, 4, 64, 64, 0.01, one, one, None, one, 8, None) != 0
+    assert b"workspace" in lib.tcl_last_error()
+    assert lib.tcl_flow_ids_workspace_bytes(300, 720, 1280) >= 300 * (720 * 1280 // 2048) * 4
+    assert lib.tcl_unique_inverse_workspace_bytes(1 << 20) >= (1 << 20) * 4
+    assert lib.tcl_unique_inverse(one, 10, 1 << 31, one, None, one, 1 << 40, None) != 0
+    # softmax: pitch must cover the columns and be a multiple of 8
+    assert lib.tcl_softmax_rows(0, one, 4, 100, 96, None) != 0
+    assert lib.tcl_softmax_rows(0, one, 4, 100, 101, None) != 0
+    assert lib.tcl_softmax_rows(7, one, 4, 100, 104, None) != 0 and b"dtype" in lib.tcl_last_error()
+    # staging: channel padding smaller than the channel count
+    assert lib.tcl_image_to_nhwc(0, 0, one, 1, 3, 8, 8, 2, 1.0, 0.0, one, None) != 0
+    # DDIM step: mu_in == 0 would divide by zero
+    assert lib.tcl_ddim_next(1, one, one, one, 16, 0.0, 1.0, 1.0, 0.0, None) != 0 and b"mu_in" in lib.tcl_last_error()
+    # attention: unsupported head padding
+    a = _lib.AttnDesc()
+    a.dtype, a.batch, a.heads, a.tq, a.tk, a.d, a.d_pad, a.kv_batch_div = 1, 1, 1, 8, 8, 40, 96, 1
+    a.tq_pitch = a.tk_pitch = 8
+    a.q = a.k = a.vt = a.out = 16
+    assert lib.tcl_attention(C.byref(a), None) != 0 and b"d_pad" in lib.tcl_last_error()
+    # the tuning hook is a plain setter
+    old = lib.tcl_debug_attention_variant(5)
+    assert lib.tcl_debug_attention_variant(old) == 5
