@@ -160,8 +160,9 @@ def run_reference(args):
         "impl": "reference", "metric": "denoising_steps_per_sec", "value": sps, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / sps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.frames}f@{args.height}x{args.width} multi-axis+VidToMe, 25-step schedule",
-                   "note": "reference is Python/PyTorch: timed = oracle port of its CPU path (oracle/unet_ref.py)"},
+        "config": {"workload": f"{args.frames}f@{args.height}x{args.width} multi-axis denoising + VidToMe (chunk 4, mix-4, 0.6/0.5), L=154/77, guidance 2.0",
+                   "unit_def": "step = one full-video multi-axis denoising step",
+                   "note": "reference is Python/PyTorch: timed = oracle port of its CPU path (oracle/unet_ref.py), bounded sample extrapolated by the FLOP model"},
         "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
                          "sample": f"1-frame xy chunk-forward (2 images, L=154) = {sec:.2f} s; extrapolated x{ratio:.0f} by the FLOP model"},
         "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
