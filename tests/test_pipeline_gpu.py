@@ -70,11 +70,3 @@ def test_relight_end_to_end_vs_oracle_chain(cuda):
     # the decoded video up to the exposure / UVT adjustments (measured 2.7e-2 mean-abs)
     assert (out - dec.clamp(0, 1)).abs().mean().item() < 6e-2
 
-
-def test_run_cli_synthetic(cuda, capsys):
-    """`python -m tclight_b200.run --synthetic --small`: model_utils.init_synthetic -> Generator.relight end to end."""
-    from tclight_b200 import run
-
-    rc = run.main(["--synthetic", "--small", "--frames", "5", "--height", "176", "--width", "192", "--steps", "2", "--opt_epochs", "1"])
-    out = capsys.readouterr().out
-    assert rc == 0 and "finite=True" in out and "(5, 3, 176, 192)" in out
