@@ -280,6 +280,34 @@ class Generator(VidToMeGenerator):
 
     # ---------------------------------------------------------------- pipeline level (generate.py:179-190, 552-630)
     @torch.no_grad()
+    def encode_prompt_inner(self, txt: str):
+        """generate.py:97-115: tokenise without truncation, cut into (model_max_length - 2)-token chunks, wrap each in
+        BOS/EOS, pad with EOS, run the text encoder on all chunks -> [n_chunks, 77, 768]."""
+        if self.tokenizer is None or self.text_encoder is None:
+            raise TclError("Generator: pipe.tokenizer / pipe.text_encoder are required to encode prompts")
+        max_length = self.tokenizer.model_max_length
+        chunk_length = max_length - 2
+        id_start, id_end = self.tokenizer.bos_token_id, self.tokenizer.eos_token_id
+        tokens = self.tokenizer(txt, truncation=False, add_special_tokens=False)["input_ids"]
+        chunks = []
+        for i in range(0, len(tokens), chunk_length):
+            ck = [id_start] + tokens[i:i + chunk_length] + [id_end]
+            chunks.append(ck[:max_length] if len(ck) >= max_length else ck + [id_end] * (max_length - len(ck)))
+        token_ids = torch.tensor(chunks).to(device=self.device, dtype=torch.int64)
+        return self.text_encoder(token_ids).last_hidden_state
+
+    @torch.no_grad()
+    def encode_prompt_pair(self, positive_prompt, negative_prompt):
+        """generate.py:117-135: both prompts are repeated up to the longer chunk count and their chunks concatenated
+        along the token axis -> (cond, uncond), each [1, 77*k, 768] (k = 2 for the shipped prompts: L = 154)."""
+        c = self.encode_prompt_inner(positive_prompt)
+        uc = self.encode_prompt_inner(negative_prompt)
+        max_chunk = max(len(c), len(uc))
+        c = torch.cat([c] * int(math.ceil(max_chunk / len(c))), dim=0)[:max_chunk]
+        uc = torch.cat([uc] * int(math.ceil(max_chunk / len(uc))), dim=0)[:max_chunk]
+        return c.reshape(1, -1, c.shape[-1]), uc.reshape(1, -1, uc.shape[-1])
+
+    @torch.no_grad()
     def encode_imgs_batch(self, imgs):
         """generate_utils.py:157-172: frames [N,3,H,W] in [0,1] -> latents (posterior mean * 0.18215)."""
         if self.vae is None:
@@ -357,8 +385,8 @@ class Generator(VidToMeGenerator):
         dp = self.data_parser
         if dp is None or not hasattr(dp, "load_video"):
             raise TclError("Generator.__call__ needs pipe.data_parser (load_video / load_flow); use relight() with tensors")
-        if not hasattr(self, "encode_prompt_pair"):
-            raise TclError("Generator.__call__ needs a text encoder (encode_prompt_pair); use relight() with embeddings")
+        if self.tokenizer is None or self.text_encoder is None:
+            raise TclError("Generator.__call__ needs pipe.tokenizer / pipe.text_encoder; use relight() with embeddings")
         frames = dp.load_video(frame_ids=frame_ids)
         frames = frames[0] if isinstance(frames, (tuple, list)) else frames
         self.rng = [torch.Generator(device=self.device).manual_seed(int(self.seed))] * len(frame_ids)

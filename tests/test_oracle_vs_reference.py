@@ -168,3 +168,31 @@ def test_ddim_inversion_matches_reference_inverter(ref):
         xT = P.ddim_walk(unet, sch, x, conds, 4, True)
         assert torch.equal(xT, gold["x_T"])
         assert torch.equal(P.ddim_walk(unet, sch, xT, conds, 4, False), gold["x_recon"])
+
+
+def test_encode_prompt_pair_matches_reference(ref):
+    """Generator.encode_prompt_inner / encode_prompt_pair (generate.py:97-135: chunking of long prompts into 75-token
+    pieces) on a stand-in tokenizer / text encoder: the B200 mirror returns the reference's tensors."""
+    import types
+
+    from tclight_b200.generate import Generator as Mine
+
+    class Tok:
+        model_max_length, bos_token_id, eos_token_id = 77, 1, 2
+
+        def __call__(self, txt, truncation=False, add_special_tokens=False):
+            return {"input_ids": [3 + (hash(w) % 50) for w in txt.split()]}
+
+    emb = torch.nn.Embedding(64, 16)
+    enc = lambda ids: types.SimpleNamespace(last_hidden_state=emb(ids) + torch.arange(ids.shape[1])[None, :, None] * 0.01)
+    g_ref = object.__new__(ref.generate.Generator)
+    g_mine = object.__new__(Mine)
+    for g in (g_ref, g_mine):
+        torch.nn.Module.__init__(g)
+        g.tokenizer, g.text_encoder, g.device = Tok(), enc, "cpu"
+    short = "a sunlit kitchen warm light"
+    long = " ".join(f"w{i}" for i in range(170))           # 3 chunks
+    for pos, neg in [(short, "bad"), (long, short), (short, long), (long, long)]:
+        c_ref, uc_ref = g_ref.encode_prompt_pair(pos, neg)
+        c, uc = g_mine.encode_prompt_pair(pos, neg)
+        assert c.shape == c_ref.shape and torch.equal(c, c_ref) and torch.equal(uc, uc_ref)
