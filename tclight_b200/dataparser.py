@@ -195,3 +195,51 @@ class VideoDataParser:
         N, H, W = flow_ids.shape
         self.unq_inv = flow_utils.voxelization(flow_ids.view(-1, 1), id_range=N * H * W)
         return rgbs.permute(0, 2, 3, 1).reshape(-1, 3), None, None, future_flows, past_flows, mask_bwds
+
+
+# ---- outputs (utils/VidToMe/utils.py:147-189) -----------------------------------------------------------------
+def save_frames(frames: torch.Tensor, path: str, ext: str = "png", frame_ids=None) -> None:
+    """One image file per frame, named by frame id (``0000.png`` ...)."""
+    import cv2
+
+    os.makedirs(path, exist_ok=True)
+    ids = list(range(len(frames))) if frame_ids is None else list(frame_ids)
+    for i, f in zip(ids, frames):
+        img = (f.detach().float().clamp(0, 1) * 255).to(torch.uint8).permute(1, 2, 0).cpu().numpy()
+        cv2.imwrite(os.path.join(path, "{:04}.{}".format(i, ext)), cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
+
+
+def save_video(frames: torch.Tensor, path: str, frame_ids=None, save_frame: bool = False, gif: bool = False, post_fix: str = "",
+               fps: int = 30) -> str:
+    """``output<post_fix>.mp4`` under ``path`` (OpenCV writer: torchvision.io.write_video / imageio are not available
+    here, so the container is mp4v instead of the reference's libx264 and ``gif=True`` is not supported), plus the
+    frames as PNGs when ``save_frame``.  Returns the video path."""
+    import cv2
+
+    if gif:
+        raise TclError("save_video: GIF output needs imageio (not available); use gif=False")
+    os.makedirs(path, exist_ok=True)
+    ids = list(range(len(frames))) if frame_ids is None else list(frame_ids)
+    sel = frames[ids]
+    proc = (sel.detach().float().permute(0, 2, 3, 1) * 255).to(torch.uint8).cpu().numpy()       # truncation like the reference
+    out = os.path.join(path, f"output{post_fix}.mp4")
+    h, w = proc.shape[1:3]
+    wr = cv2.VideoWriter(out, cv2.VideoWriter_fourcc(*"mp4v"), float(fps), (w, h))
+    if not wr.isOpened():
+        raise TclError(f"save_video: cannot open a writer for {out}")
+    for img in proc:
+        wr.write(cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
+    wr.release()
+    print(f"[INFO] save video to {out}")
+    if save_frame:
+        save_frames(sel, os.path.join(path, f"frames{post_fix}"), frame_ids=ids)
+    return out
+
+
+def save_loss_curve(loss_list, output_path: str, title: str = "Loss Curve") -> str:
+    """utils/general_utils.py: the reference plots with matplotlib (absent here); the values are written as text."""
+    os.makedirs(output_path, exist_ok=True)
+    p = os.path.join(output_path, f"{title}.txt")
+    with open(p, "w") as f:
+        f.write("\n".join(repr(float(v)) for v in loss_list))
+    return p

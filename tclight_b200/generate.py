@@ -397,6 +397,22 @@ class Generator(VidToMeGenerator):
         for name, prompt in self.prompt.items():
             c, u = self.encode_prompt_pair(prompt, self.negative_prompt)
             ct, ut = self.encode_prompt_pair(self.prompt_t, self.negative_prompt_t)
-            results[name] = self.relight(frames.to(self.device), torch.cat([u, c]), torch.cat([ut, ct]), flows, past,
-                                         flow_alpha=getattr(dp, "alpha", 0.5))
+            out, info = self.relight(frames.to(self.device), torch.cat([u, c]), torch.cat([ut, ct]), flows, past,
+                                     flow_alpha=getattr(dp, "alpha", 0.5))
+            results[name] = (out, info)
+            if output_path:
+                # generate.py:611-630: one folder per prompt with the relit video, the input video and the loss curves
+                import os
+                from .config_utils import save_config
+                from .dataparser import save_loss_curve, save_video
+
+                opt_suffix = "_opt" if self.apply_opt else ""
+                cur = os.path.join(output_path, f"lmr_{self.local_merge_ratio}_gmr_{self.global_merge_ratio}_alpha_t_{self.alpha_t}"
+                                                f"{opt_suffix}_{name}")
+                save_config(self.config, cur, gene=True)
+                save_video(out, cur, save_frame=self.save_frame, fps=getattr(dp, "fps", 30))
+                save_video(frames, cur, save_frame=False, post_fix="_gt", fps=getattr(dp, "fps", 30))
+                if self.apply_opt:
+                    save_loss_curve(info["loss_exposure"], cur, "loss_exposure")
+                    save_loss_curve(info["loss_unique_tensor"], cur, "loss_unique_tensor")
         return results

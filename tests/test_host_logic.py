@@ -359,3 +359,21 @@ def test_run_cli_requires_cuda_for_synthetic(capsys):
         return
     assert run.main(["--synthetic", "--small"]) == 2
     assert "CUDA device is required" in capsys.readouterr().err
+
+
+def test_save_video_and_frames_roundtrip(tmp_path):
+    import cv2
+    import torch
+    from tclight_b200 import dataparser as D
+
+    g = torch.Generator().manual_seed(0)
+    frames = torch.rand(4, 3, 32, 48, generator=g)
+    out = D.save_video(frames, str(tmp_path / "o"), save_frame=True, fps=10, post_fix="_x")
+    assert out.endswith("output_x.mp4")
+    cap = cv2.VideoCapture(out)
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 4 and int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)) == 48
+    cap.release()
+    back = D.read_frames(str(tmp_path / "o" / "frames_x"))            # PNGs are lossless: 8-bit truncation only
+    assert back.shape == frames.shape and (back - frames).abs().max() <= 1 / 255 + 1e-6
+    p = D.save_loss_curve([0.5, 0.25], str(tmp_path / "o"), "loss_exposure")
+    assert open(p).read().split() == ["0.5", "0.25"]
