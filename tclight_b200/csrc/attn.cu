@@ -75,18 +75,6 @@ __device__ __forceinline__ float poly_exp2(float x) {
   return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
 }
 
-// P (>= 0, finite) -> two 16-bit values in one register.  F2FP.PACK_AB executes on the XU pipe next to MUFU.EX2
-// (ncu: XU busy = MUFU + ~12 %), which is the binding pipe of this kernel; for bf16 the same result up to ties
-// (round half up instead of half to even) comes from two integer adds and one byte permute on the ALU pipe.
-template <bool BF16, bool IPACK>
-__device__ __forceinline__ uint32_t pack_p(float a, float b) {
-  if (BF16 && IPACK) {
-    const uint32_t ua = __float_as_uint(a) + 0x8000u, ub = __float_as_uint(b) + 0x8000u;
-    return __byte_perm(ua, ub, 0x7632);
-  }
-  return Elem<BF16>::pack(a, b);
-}
-
 // D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (P, 16-bit pairs packed in 32-bit TMEM columns, one row per
 // lane) is read straight from tensor memory, so P never crosses shared memory.
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
@@ -104,11 +92,10 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 // TS   : P is handed to the P V MMA through TMEM (tcgen05.st + A-from-TMEM MMA) instead of swizzled smem.
 // POLY : 8-bit mask over every 8 consecutive exponentials: set bits run as FMA-pipe polynomials (poly_exp2)
 //        instead of MUFU.EX2.
-// STAG : softmax warpgroup q starts q*STAG clocks late, so the warpgroups' MUFU phases interleave.
 // SPLIT: softmax warpgroups per Q tile.  With 2, each thread owns one row x 64 score columns and the two halves
 //        exchange their row maxima through shared memory: 4 softmax warps per scheduler instead of 2 keep the XU
 //        pipe (MUFU.EX2 + F2FP, the binding pipe) busy while other warps sit in their load / max / store phases.
-template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS, int POLY, int STAG, bool IPACK, int SPLIT, int MINB>
+template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS, int POLY, int SPLIT, int MINB>
 __global__ void __launch_bounds__(NQ * 128 * SPLIT + 32 + NQ * 32, MINB)
 attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnParams p) {
   using E = Elem<BF16>;
@@ -295,10 +282,6 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
     const uint32_t p_tile_addr = smem_u32(smem + OFF_P + (TS ? 0 : q * P_TILE));
     const uint32_t t_p = t_lane + TMEM_P + q * 64 + half * (COLS / 2);
     const bool tracer = threadIdx.x == q * 128 * SPLIT;
-    if (STAG > 0 && q > 0) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < (long long)STAG * q) {}
-    }
     // A barrier probe costs ~250 clk even when the phase is long complete (measured with the clock64 trace), so
     // both per-tile barriers are probed early with the non-blocking form and the result is consumed later: the
     // blocking wait only runs when the early probe failed.
@@ -374,7 +357,7 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
           const float a1 = fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_ref);
           const float e0 = ((POLY >> (i & 7)) & 1) ? poly_exp2<BF16>(a0) : fast_exp2(a0);
           const float e1 = ((POLY >> ((i + 1) & 7)) & 1) ? poly_exp2<BF16>(a1) : fast_exp2(a1);
-          pk[(c0 + i) >> 1] = pack_p<BF16, IPACK>(e0, e1);
+          pk[(c0 + i) >> 1] = E::pack(e0, e1);
         }
       };
       do_chunk(s0, 0);
@@ -472,14 +455,13 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
   }
 }
 
-template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS = false, int POLY = 0, int STAG = 0, bool IPACK = false, int SPLIT = 1,
-          int MINB = 1>
+template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS = false, int POLY = 0, int SPLIT = 1, int MINB = 1>
 static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, int bh, cudaStream_t stream) {
   constexpr size_t smem = (size_t)NQ * 128 * DPAD * 2 + (size_t)KST * 128 * DPAD * 2 +
                           (size_t)VST * 2 * DPAD * 128 + (TS ? 0 : (size_t)NQ * 128 * 128 * 2) + 1024 + 256 + 4096;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG, IPACK, SPLIT, MINB>,
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, SPLIT, MINB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_last_error("attention: cudaFuncSetAttribute(%zu B) failed: %s", smem, cudaGetErrorString(e));
@@ -488,7 +470,7 @@ static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, in
     configured = true;
   }
   dim3 grid((q_tiles + NQ - 1) / NQ, bh);
-  attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, STAG, IPACK, SPLIT, MINB><<<grid, NQ * 128 * SPLIT + 32 + NQ * 32, smem, stream>>>(tm, p);
+  attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, SPLIT, MINB><<<grid, NQ * 128 * SPLIT + 32 + NQ * 32, smem, stream>>>(tm, p);
   TCL_CHECK_LAUNCH("tcl_attention");
   return TCL_OK;
 }
@@ -549,28 +531,28 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
     // loads, two serial tiles, epilogue) dominates, so run one Q tile per CTA and two CTAs per SM (256 TMEM columns,
     // 85 KB of shared memory each) to overlap the chains of neighbouring tiles
     if (var >= 1 && var != 8 && a->tk <= 256) {
-      return bf16 ? launch_attn<1, 64, 2, 2, true, true, 0x03, 0, false, 1, 2>(tm, p, q_tiles, bh, stream)
-                  : launch_attn<1, 64, 2, 2, false, true, 0x00, 0, false, 1, 2>(tm, p, q_tiles, bh, stream);
+      return bf16 ? launch_attn<1, 64, 2, 2, true, true, 0x03, 1, 2>(tm, p, q_tiles, bh, stream)
+                  : launch_attn<1, 64, 2, 2, false, true, 0x00, 1, 2>(tm, p, q_tiles, bh, stream);
     }
     if (!bf16) {
-      if (var >= 3) return launch_attn<2, 64, 4, 3, false, true, 0, 0, false, 2>(tm, p, q_tiles, bh, stream);
+      if (var >= 3) return launch_attn<2, 64, 4, 3, false, true, 0, 2>(tm, p, q_tiles, bh, stream);
       return var >= 1 ? launch_attn<2, 64, 4, 3, false, true>(tm, p, q_tiles, bh, stream)
                       : launch_attn<2, 64, 3, 2, false>(tm, p, q_tiles, bh, stream);
     }
     switch (var) {
-      case 1: return launch_attn<2, 64, 4, 3, true, true, 0x00, 0>(tm, p, q_tiles, bh, stream);
-      case 2: case 8: return launch_attn<2, 64, 4, 3, true, true, 0x03, 0>(tm, p, q_tiles, bh, stream);
-      case 3: return launch_attn<2, 64, 4, 3, true, true, 0x00, 0, false, 2>(tm, p, q_tiles, bh, stream);
-      case 4: return launch_attn<2, 64, 4, 3, true, true, 0x03, 0, false, 2>(tm, p, q_tiles, bh, stream);
-      case 5: return launch_attn<2, 64, 4, 3, true, true, 0x13, 0, false, 2>(tm, p, q_tiles, bh, stream);
-      case 6: return launch_attn<2, 64, 4, 3, true, true, 0x33, 0, false, 2>(tm, p, q_tiles, bh, stream);
-      case 7: return launch_attn<2, 64, 4, 3, true, true, 0x11, 0, false, 2>(tm, p, q_tiles, bh, stream);
+      case 1: return launch_attn<2, 64, 4, 3, true, true, 0x00>(tm, p, q_tiles, bh, stream);
+      case 2: case 8: return launch_attn<2, 64, 4, 3, true, true, 0x03>(tm, p, q_tiles, bh, stream);
+      case 3: return launch_attn<2, 64, 4, 3, true, true, 0x00, 2>(tm, p, q_tiles, bh, stream);
+      case 4: return launch_attn<2, 64, 4, 3, true, true, 0x03, 2>(tm, p, q_tiles, bh, stream);
+      case 5: return launch_attn<2, 64, 4, 3, true, true, 0x13, 2>(tm, p, q_tiles, bh, stream);
+      case 6: return launch_attn<2, 64, 4, 3, true, true, 0x33, 2>(tm, p, q_tiles, bh, stream);
+      case 7: return launch_attn<2, 64, 4, 3, true, true, 0x11, 2>(tm, p, q_tiles, bh, stream);
       default: return launch_attn<2, 64, 3, 2, true>(tm, p, q_tiles, bh, stream);
     }
   } else if (a->d_pad == 128) {
     if (var >= 3)
-      return bf16 ? launch_attn<1, 128, 3, 2, true, true, 0, 0, false, 2>(tm, p, q_tiles, bh, stream)
-                  : launch_attn<1, 128, 3, 2, false, true, 0, 0, false, 2>(tm, p, q_tiles, bh, stream);
+      return bf16 ? launch_attn<1, 128, 3, 2, true, true, 0, 2>(tm, p, q_tiles, bh, stream)
+                  : launch_attn<1, 128, 3, 2, false, true, 0, 2>(tm, p, q_tiles, bh, stream);
     if (var >= 1)
       return bf16 ? launch_attn<1, 128, 3, 2, true, true>(tm, p, q_tiles, bh, stream)
                   : launch_attn<1, 128, 3, 2, false, true>(tm, p, q_tiles, bh, stream);
@@ -578,8 +560,8 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
                 : launch_attn<1, 128, 2, 2, false>(tm, p, q_tiles, bh, stream);
   } else {
     if (var >= 3)
-      return bf16 ? launch_attn<1, 192, 2, 1, true, true, 0, 0, false, 2>(tm, p, q_tiles, bh, stream)
-                  : launch_attn<1, 192, 2, 1, false, true, 0, 0, false, 2>(tm, p, q_tiles, bh, stream);
+      return bf16 ? launch_attn<1, 192, 2, 1, true, true, 0, 2>(tm, p, q_tiles, bh, stream)
+                  : launch_attn<1, 192, 2, 1, false, true, 0, 2>(tm, p, q_tiles, bh, stream);
     if (var >= 1)
       return bf16 ? launch_attn<1, 192, 2, 1, true, true>(tm, p, q_tiles, bh, stream)
                   : launch_attn<1, 192, 2, 1, false, true>(tm, p, q_tiles, bh, stream);
