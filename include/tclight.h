@@ -115,7 +115,7 @@ typedef struct {
 
 int tcl_attention(const tcl_attn_desc* desc, tcl_stream_t stream);
 /* tuning hook: kernel variant used by tcl_attention (0 = P staged through shared memory, >= 1 = P handed to the
- * P V MMA through tensor memory, with different exp2 / warpgroup-stagger settings); returns the previous value */
+ * P V MMA through tensor memory, with different exp2 shares / column-split softmax); returns the previous value */
 int tcl_debug_attention_variant(int variant);
 /* debug hook, active only in -DTCL_ATTN_TRACE builds: device int64[192] event log (see attn.cu) */
 void tcl_debug_attention_trace(long long* buf);

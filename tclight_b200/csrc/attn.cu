@@ -571,7 +571,7 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
 }
 
 // Tuning hook: selects the kernel variant used by tcl_attention (0 = P through shared memory; 1.. = P through
-// TMEM with different exp2 / stagger settings, see the dispatch above).  Returns the previous value.
+// TMEM with different exp2 shares / column-split softmax, see the dispatch above).  Returns the previous value.
 extern "C" int tcl_debug_attention_variant(int v) {
   const int old = g_attn_variant;
   g_attn_variant = v;
