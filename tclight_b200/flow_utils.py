@@ -10,7 +10,6 @@ the reference's CPU path does; its CUDA ``index_put_`` picks an unspecified one)
 """
 from __future__ import annotations
 
-import ctypes as C
 
 import torch
 

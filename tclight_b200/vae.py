@@ -18,12 +18,11 @@ Activations are NHWC 16-bit; 3 / 4 / 8-channel tensors are padded to 64 channels
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 import torch.nn as nn
 
-from . import _lib as L
 from . import ops
 from ._lib import TclError, check, dtype_code, latent_code, lib, require_cuda, stream_ptr
 from .weights import pack_conv3x3
@@ -31,14 +30,6 @@ from .weights import pack_conv3x3
 
 def _f32(t, dev):
     return t.detach().to(device=dev, dtype=torch.float32).contiguous()
-
-
-def _pad_rows(w: torch.Tensor, rows: int) -> torch.Tensor:
-    if w.shape[0] >= rows:
-        return w
-    out = torch.zeros((rows,) + tuple(w.shape[1:]), dtype=w.dtype)
-    out[: w.shape[0]] = w
-    return out
 
 
 class _Conv:
