@@ -114,6 +114,85 @@ def ddim_sample_oracle(unet, x, conds, conds_t, concat_conds, n_timesteps=25, al
     return x
 
 
+class RankRng:
+    """Host RNG streams of one emulated rank (np.random + torch CPU): every process of a multi-GPU run owns its
+    own streams, all seeded identically, and consumes them at its own pace."""
+
+    def __init__(self, seed: int):
+        self.np_state = np.random.RandomState(seed).get_state()
+        g = torch.Generator().manual_seed(seed)
+        self.torch_state = g.get_state()
+
+    def __enter__(self):
+        self._saved = (np.random.get_state(), torch.get_rng_state())
+        np.random.set_state(self.np_state)
+        torch.set_rng_state(self.torch_state)
+        return self
+
+    def __exit__(self, *a):
+        self.np_state, self.torch_state = np.random.get_state(), torch.get_rng_state()
+        np.random.set_state(self._saved[0])
+        torch.set_rng_state(self._saved[1])
+        return False
+
+
+def shard_range(n: int, rank: int, world: int):
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+@torch.no_grad()
+def ddim_sample_oracle_sharded(unets, x, conds, conds_t, concat_conds, world, n_timesteps=25, alpha_t=0.0,
+                               final_factor_t=0.01, win_size_t=64, guidance_scale=2.0, chunk_size=4, chunk_ord="mix-4",
+                               local_merge_ratio=0.6, global_merge_ratio=0.5, global_rand=0.5, rng=None, seed=12345):
+    """The multi-GPU semantics of SURVEY.md §8(e): "the reference with the global-token pool reset at shard
+    boundaries".  Rank r of `world` runs the reference loop body (generate.py:216-237) on frames
+    [N r / world, N (r+1) / world) in the xy pass and on latent columns [W r / world, W (r+1) / world) in the yt pass,
+    with its OWN VidToMe pool / module generators (`unets[r]`: one patched oracle UNet per rank, identical weights)
+    and its own host RNG streams (seeded alike); AdaIN, blend and the scheduler step are replicated.  world == 1 is
+    `ddim_sample_oracle`."""
+    assert len(unets) == world
+    for u in unets:
+        if not hasattr(u, "_oracle_tome"):
+            apply_oracle_patch(u, local_merge_ratio, True, global_merge_ratio, global_rand=global_rand)
+    perm_div = float(chunk_ord.split("-")[-1]) if "-" in chunk_ord else 3.0
+    ord_kind = "mix" if "mix" in chunk_ord else chunk_ord
+    rngs = [RankRng(seed) for _ in range(world)]
+    sched = DPMSolverSDEKarras()
+    sched.set_timesteps(n_timesteps, device=x.device)
+    steps = sched.timesteps
+    N, W = len(x), x.shape[-1]
+    for i, t in enumerate(steps):
+        noises = torch.zeros_like(x)
+        for r in range(world):
+            f0, f1 = shard_range(N, r, world)
+            with rngs[r]:
+                for part in plan_chunks(f1 - f0, chunk_size, True, ord_kind, perm_div):
+                    part = part + f0
+                    noises[part] = cfg_noise(unets[r], x[part], conds, t, concat_conds[part], guidance_scale)
+        if alpha_t > 0:
+            a = alpha_t * final_factor_t ** min(i / len(steps), 1)
+            starts, overlaps = window_plan(N, win_size_t)
+            noises_t = torch.zeros_like(x)
+            for r in range(world):
+                w0, w1 = shard_range(W, r, world)
+                with rngs[r]:
+                    cols = [c + w0 for c in plan_chunks(w1 - w0, chunk_size, True, ord_kind, perm_div)]
+                    for wi, s in enumerate(starts):
+                        for part in cols:
+                            xt = x[s:s + win_size_t][:, :, :, part].permute(3, 1, 0, 2)
+                            ct = concat_conds[s:s + win_size_t][:, :, :, part].permute(3, 1, 0, 2)
+                            pred = cfg_noise(unets[r], xt, conds_t, t, ct, guidance_scale)
+                            noises_t[s:s + win_size_t, :, :, part] = pred.permute(2, 1, 3, 0)
+                        if s > 0:
+                            noises_t[s:s + overlaps[wi - 1], :, :, w0:w1] *= np.sqrt(0.5)
+            noises_t = adain(noises_t, noises)
+            noises = (a ** 0.5) * noises_t + ((1 - a) ** 0.5) * noises
+        x = sched.step(noises, t, x, generator=rng)[0]
+        for u in unets:
+            reset_oracle_pool(u)
+    return x
+
+
 # ---------------------------------------------------------------------------------------------
 # DDIM inversion / reconstruction (reference invert.py:151-188, 215-244) as plain functions
 # ---------------------------------------------------------------------------------------------

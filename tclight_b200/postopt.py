@@ -345,29 +345,3 @@ def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: i
             "loss_first_last": [losses[3, 0].item(), losses[(3 + iters - 1) % len(losses), 0].item()], "n_gpus": world,
             "parallelism": f"batch-parallel x{world}, NCCL all-reduce of the [U,3] gradient" if world > 1 else "single GPU",
             "note": "dense-Adam semantics (every UVT row updated every iteration, as torch.optim.Adam does)"}
-
-
-def smoke_check(device):
-    """One stage-2 and one stage-1 iteration on a tiny clip, checked against the oracle."""
-    import types
-
-    from oracle import postopt_ref as O
-
-    edited, flows, masks, inv = O.synthetic_clip(n=5, h=176, w=192, seed=1, device=device)
-    ds = OptDataset(edited.clone(), flows, masks, device=device)
-    gen = types.SimpleNamespace(dataset=ds, data_parser=types.SimpleNamespace(unq_inv=inv), lambda_dssim=0.2, lambda_flow=0.8,
-                                lambda_tv=0.05, epochs_exposure=1, epochs=1, opt_batch_size=4, feature_lr=0.05, exposure_lr_init=0.01,
-                                exposure_lr_final=0.001, exposure_lr_delay_steps=0, exposure_lr_delay_mult=0.0)
-    torch.manual_seed(5)
-    _, got = unique_tensor_optimization(gen)
-    torch.manual_seed(5)
-    _, _, want = O.stage2_uvt(edited, flows, masks, inv, O.draw_batches(5, 4, 1))
-    d2 = max(abs(a - b) for a, b in zip(got, want))
-    torch.manual_seed(6)
-    _, got1 = exposure_align(gen)
-    torch.manual_seed(6)
-    _, _, want1 = O.stage1_exposure(edited, flows, masks, O.draw_batches(5, 4, 1))
-    d1 = max(abs(a - b) for a, b in zip(got1, want1))
-    print(f"[smoke] path 2: stage-2 loss diff vs oracle {d2:.2e}, stage-1 {d1:.2e}")
-    if not (d2 < 1e-5 and d1 < 1e-5):
-        raise RuntimeError("smoke: optimiser parity failed")

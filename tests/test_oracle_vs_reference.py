@@ -196,3 +196,70 @@ def test_encode_prompt_pair_matches_reference(ref):
         c_ref, uc_ref = g_ref.encode_prompt_pair(pos, neg)
         c, uc = g_mine.encode_prompt_pair(pos, neg)
         assert c.shape == c_ref.shape and torch.equal(c, c_ref) and torch.equal(uc, uc_ref)
+
+
+def test_oracle_unet_matches_reference_pnp_restatements(ref):
+    """Pins the restated UNet arithmetic (oracle/unet_ref.py — diffusers is not vendored) to the reference's OWN
+    restatements of it: ``register_attention_control`` re-implements Attention.forward (to_q/k/v, head split,
+    QK^T * scale, softmax, PV, head merge, to_out) on the decoder attn1 modules and ``register_conv_control``
+    re-implements ResnetBlock2D.forward on up_blocks[1].resnets[1] (utils/VidToMe/pnp_utils.py:40-172).  With an
+    empty injection schedule they are pure re-statements; swapping them into the oracle UNet must not change its
+    output.  The diffusers-API attributes those closures read are attached as thin adapters."""
+    import importlib
+    import os
+    import types
+
+    import torch.nn.functional as F
+    from oracle.unet_ref import Attention, ResnetBlock2D, make_unet
+
+    cwd = os.getcwd()
+    os.chdir(refshim.REF_ROOT)
+    try:
+        pnp = importlib.import_module("utils.VidToMe.pnp_utils")
+    finally:
+        os.chdir(cwd)
+
+    kw = dict(block_out_channels=(64, 128, 256, 256), cross_attention_dim=64)
+    unet = make_unet(seed=0, **kw)
+    torch.manual_seed(11)
+    Fr, h, w = 2, 12, 20                       # odd pyramid: exercises upsample_size
+    x = torch.randn(2 * Fr, 4, h, w)
+    cc = torch.randn(Fr, 4, h, w) * 0.2
+    ehs = torch.randn(2 * Fr, 20, 64)
+    t = torch.tensor(801)
+    with torch.no_grad():
+        want = unet(x, t, encoder_hidden_states=ehs, cross_attention_kwargs={"concat_conds": cc}).sample
+
+    def head_to_batch_dim(self, tensor):       # diffusers Attention.head_to_batch_dim: [B, N, C] -> [B*h, N, C/h]
+        B, N, C = tensor.shape
+        return tensor.reshape(B, N, self.heads, C // self.heads).permute(0, 2, 1, 3).reshape(B * self.heads, N, C // self.heads)
+
+    def batch_to_head_dim(self, tensor):       # inverse: [B*h, N, d] -> [B, N, h*d]
+        Bh, N, d = tensor.shape
+        return tensor.reshape(Bh // self.heads, self.heads, N, d).permute(0, 2, 1, 3).reshape(Bh // self.heads, N, self.heads * d)
+
+    n_attn = n_res = 0
+    for m in unet.modules():
+        if isinstance(m, Attention):
+            m.head_to_batch_dim = types.MethodType(head_to_batch_dim, m)
+            m.batch_to_head_dim = types.MethodType(batch_to_head_dim, m)
+            m.scale = (m.to_q.out_features // m.heads) ** -0.5
+            n_attn += 1
+        if isinstance(m, ResnetBlock2D):
+            m.nonlinearity = F.silu
+            m.upsample = m.downsample = None
+            m.time_embedding_norm = "default"
+            m.dropout = torch.nn.Identity()
+            m.output_scale_factor = 1.0
+            n_res += 1
+    assert n_attn == 32 and n_res == 22
+    model = types.SimpleNamespace(unet=unet)
+    pnp.register_attention_control(model, [], 2)      # replaces attn1.forward on 8 decoder blocks
+    pnp.register_conv_control(model, [], 2)           # replaces up_blocks[1].resnets[1].forward
+    pnp.register_time(model, 801)
+    assert "forward" in unet.up_blocks[2].attentions[0].transformer_blocks[0].attn1.__dict__
+    assert "forward" in unet.up_blocks[1].resnets[1].__dict__
+    with torch.no_grad():
+        got = unet(x, t, encoder_hidden_states=ehs, cross_attention_kwargs={"concat_conds": cc}).sample
+    err = ((got - want).norm() / want.norm()).item()
+    assert err < 2e-6, err                           # einsum+softmax vs SDPA: fp32 round-off only

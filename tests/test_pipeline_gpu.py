@@ -62,11 +62,22 @@ def test_relight_end_to_end_vs_oracle_chain(cuda):
     rel = ((info["latent"].float() - lat).norm() / lat.norm()).item()
     print(f"end-to-end latent rel-L2 vs oracle chain: {rel:.3e}")
     assert rel < 8e-2
-    dec = V.decode_latents(ref_vae, lat)
+    dec = V.decode_latents(ref_vae, lat).clamp(0, 1)
     # integer part: identical inputs => identical ids (device masks fed to the oracle's id propagation)
     ids_ref = R.flow_ids(frames.cpu(), fwd.cpu(), info["mask_bwds"].cpu(), rgb_threshold=0.05)
     assert torch.equal(info["unq_inv"].cpu().view(N, H, W).to(torch.int32), ids_ref)
-    # sanity only (stage 1/2 parity is tests/test_postopt_gpu.py): after 2+2 optimiser iterations the output is still
-    # the decoded video up to the exposure / UVT adjustments (measured 2.7e-2 mean-abs)
-    assert (out - dec.clamp(0, 1)).abs().mean().item() < 6e-2
-
+    # ---- the optimiser on the ORACLE's decoded frames (same DataLoader draws: the global CPU RNG has advanced
+    # identically on both sides), so the FINAL frames are compared with the oracle chain's final frames ----
+    masks_ref = R.soft_mask_bwds(frames * 2 - 1, fwd, bwd, alpha=0.5)
+    inv_ref = R.unique_inverse(R.flow_ids(frames.cpu(), fwd.cpu(), masks_ref.cpu(), rgb_threshold=0.05)).to(cuda)
+    b1 = O.draw_batches(N, 4, 1)
+    aligned, _, loss1 = O.stage1_exposure(dec.float(), bwd, masks_ref, b1)
+    b2 = O.draw_batches(N, 4, 1)
+    final, _, loss2 = O.stage2_uvt(aligned, bwd, masks_ref, inv_ref, b2)
+    d_final = (out - final).abs().mean().item()
+    d_l1 = max(abs(a - b) for a, b in zip(info["loss_exposure"], loss1))
+    d_l2 = max(abs(a - b) for a, b in zip(info["loss_unique_tensor"], loss2))
+    print(f"end-to-end final frames mean-abs vs oracle chain {d_final:.3e}; stage-1/2 loss diffs {d_l1:.2e} / {d_l2:.2e}")
+    # Measured on the B200: latent rel-L2 2.7e-2 (fp16 UNet + VAE, discrete merges, 2 steps), final frames mean-abs
+    # 9e-3 on [0,1] images.  Bounds = 3x measured.
+    assert d_final < 3e-2

@@ -70,42 +70,98 @@ def test_adain_blend_matches_reference_ops(cuda, ldt):
     assert (b2.float() - bl.float()).abs().max().item() <= tol * bl.float().abs().max().item()
 
 
-def test_ddim_sample_multi_axis_vs_oracle(cuda):
-    from oracle import pipeline_ref as P
+def _seed_all():
+    torch.manual_seed(12345)
+    torch.cuda.manual_seed(12345)
+    np.random.seed(12345)
+
+
+def _sampler_pair(cuda, adt, ukw, **gen_kw):
+    """(oracle UNet fp32, B200 Generator in activation dtype `adt`) with identical seeded weights."""
     from oracle.unet_ref import make_unet
     from tclight_b200.config_utils import default_config
     from tclight_b200.generate import Generator
     from tclight_b200.scheduler import DPMSolverMultistepSchedulerB200
     from tclight_b200.unet import UNetB200
 
-    kw = dict(block_out_channels=(64, 128, 256, 256), cross_attention_dim=768)
-    ref_unet = make_unet(seed=0, **kw).to(cuda)
+    ref_unet = make_unet(seed=0, **ukw).to(cuda)
     sd = {k: v.detach().cpu() for k, v in ref_unet.state_dict().items()}
-    mine_unet = UNetB200(sd, device=cuda, dtype=torch.float16, block_out_channels=kw["block_out_channels"])
-    cfg = default_config(n_timesteps=4, alpha_t=0.01, win_size_t=6)
-    cfg.float_precision = "fp32"       # latents in fp32 on both sides; UNet activations fp16 vs fp32
+    mine_unet = UNetB200(sd, device=cuda, dtype=adt, block_out_channels=ukw.get("block_out_channels", (320, 640, 1280, 1280)))
+    cfg = default_config(**gen_kw)
+    cfg.float_precision = "fp32"       # latents in fp32 on both sides; UNet activations 16-bit vs the fp32 oracle
     pipe = type("Pipe", (), {})()
     pipe.unet = mine_unet
-    gen = Generator(pipe, DPMSolverMultistepSchedulerB200(), cfg)
-    N, h, w = 8, 16, 16
-    torch.manual_seed(7)
+    return ref_unet, Generator(pipe, DPMSolverMultistepSchedulerB200(), cfg)
+
+
+def _inputs(cuda, N, h, w, seed=7):
+    torch.manual_seed(seed)
     x = torch.randn(1, 4, h, w, device=cuda).repeat(N, 1, 1, 1)
     base = torch.randn(1, 4, h, w, device=cuda)
     cc = 0.18215 * (base + 0.1 * torch.randn(N, 4, h, w, device=cuda))
     conds = torch.randn(2, 154, 768, device=cuda)
     conds_t = torch.randn(2, 77, 768, device=cuda)
+    return x, cc, conds, conds_t
 
-    def seed_all():
-        torch.manual_seed(12345)
-        torch.cuda.manual_seed(12345)
-        np.random.seed(12345)
 
-    seed_all()
+# Loop-level bounds are <= 3x the error measured on the B200 (recorded next to each bound); the discrete VidToMe
+# decisions make the error of a multi-step run heavy-tailed, so the measured value is printed for the record.
+@pytest.mark.parametrize("adt,tol", [(torch.float16, 1.5e-2), (torch.bfloat16, 6e-2)])
+def test_ddim_sample_multi_axis_vs_oracle(cuda, adt, tol):
+    """4 steps, 8 frames, multi-axis, VidToMe on, tiny widths.  Measured: fp16 5.0e-3, bf16 2.2e-2."""
+    from oracle import pipeline_ref as P
+
+    ref_unet, gen = _sampler_pair(cuda, adt, dict(block_out_channels=(64, 128, 256, 256), cross_attention_dim=768),
+                                  n_timesteps=4, alpha_t=0.01, win_size_t=6)
+    N, h, w = 8, 16, 16
+    x, cc, conds, conds_t = _inputs(cuda, N, h, w)
+    _seed_all()
     gen.rng = [torch.Generator(device=cuda).manual_seed(12345)] * N
-    got = gen.ddim_sample(x.clone(), conds.half(), conds_t.half(), cc)
-    seed_all()
+    got = gen.ddim_sample(x.clone(), conds.to(adt), conds_t.to(adt), cc)
+    _seed_all()
     want = P.ddim_sample_oracle(ref_unet, x.clone(), conds, conds_t, cc, n_timesteps=4, alpha_t=0.01, win_size_t=6,
                                 rng=[torch.Generator(device=cuda).manual_seed(12345)] * N)
     err = rel_l2(got, want)
-    print(f"multi-axis ddim_sample (4 steps, 8 frames, VidToMe on): rel-L2 {err:.3e}")
-    assert err < 5e-2
+    print(f"multi-axis ddim_sample {adt} (4 steps, 8 frames, VidToMe on): rel-L2 {err:.3e}")
+    assert err < tol
+
+
+@pytest.mark.parametrize("adt,tol", [(torch.float16, 1.5e-2), (torch.bfloat16, 6e-2)])
+def test_baseline_config1_sd15_widths(cuda, adt, tol):
+    """BASELINE.json configs[0] exactly: 8 frames, 256x256 (latent 32x32), 4 denoising steps, single axis,
+    **SD-1.5 widths** (320/640/1280/1280: ds-1 merging at head dim 40, ds-2 at head dim 80), VidToMe on, L = 154 —
+    B200 path vs the oracle loop on the same seeds."""
+    from oracle import pipeline_ref as P
+
+    ref_unet, gen = _sampler_pair(cuda, adt, {}, n_timesteps=4, alpha_t=0.0)
+    N, h, w = 8, 32, 32
+    x, cc, conds, conds_t = _inputs(cuda, N, h, w, seed=11)
+    _seed_all()
+    gen.rng = [torch.Generator(device=cuda).manual_seed(12345)] * N
+    got = gen.ddim_sample(x.clone(), conds.to(adt), conds_t.to(adt), cc)
+    _seed_all()
+    want = P.ddim_sample_oracle(ref_unet, x.clone(), conds, conds_t, cc, n_timesteps=4, alpha_t=0.0,
+                                rng=[torch.Generator(device=cuda).manual_seed(12345)] * N)
+    err = rel_l2(got, want)
+    print(f"config 1 (8f 256x256, 4 steps, single axis, SD-1.5 widths) {adt}: rel-L2 {err:.3e}")
+    assert err < tol
+
+
+@pytest.mark.parametrize("adt,tol", [(torch.float16, 1.5e-2), (torch.bfloat16, 6e-2)])
+def test_multi_axis_step_sd15_widths(cuda, adt, tol):
+    """One full multi-axis step (xy pass + yt pass over 2 overlapping windows + AdaIN/blend + DPM-Solver++ update) at
+    SD-1.5 widths: the yt 'images' are (frames x height) = 6x32 per latent column."""
+    from oracle import pipeline_ref as P
+
+    ref_unet, gen = _sampler_pair(cuda, adt, {}, n_timesteps=2, alpha_t=0.01, win_size_t=6)
+    N, h, w = 8, 32, 32
+    x, cc, conds, conds_t = _inputs(cuda, N, h, w, seed=13)
+    _seed_all()
+    gen.rng = [torch.Generator(device=cuda).manual_seed(12345)] * N
+    got = gen.ddim_sample(x.clone(), conds.to(adt), conds_t.to(adt), cc)
+    _seed_all()
+    want = P.ddim_sample_oracle(ref_unet, x.clone(), conds, conds_t, cc, n_timesteps=2, alpha_t=0.01, win_size_t=6,
+                                rng=[torch.Generator(device=cuda).manual_seed(12345)] * N)
+    err = rel_l2(got, want)
+    print(f"multi-axis, SD-1.5 widths, 2 steps {adt}: rel-L2 {err:.3e}")
+    assert err < tol
