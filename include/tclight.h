@@ -114,9 +114,10 @@ typedef struct {
 } tcl_attn_desc;
 
 int tcl_attention(const tcl_attn_desc* desc, tcl_stream_t stream);
-/* tuning hook: kernel variant used by tcl_attention (0 = P staged through shared memory, >= 1 = P handed to the
- * P V MMA through tensor memory, with different exp2 shares / column-split softmax); returns the previous value */
+/* tuning hooks (tools/bench_attn_variants.py): kernel variant used by tcl_attention (-1 = shipped configuration; see the
+ * dispatch in csrc/attn.cu) and trimming of the MMA shapes to the live head-dim columns; return the previous value */
 int tcl_debug_attention_variant(int variant);
+int tcl_debug_attention_trim(int on);
 /* debug hook, active only in -DTCL_ATTN_TRACE builds: device int64[192] event log (see attn.cu) */
 void tcl_debug_attention_trace(long long* buf);
 

@@ -249,6 +249,8 @@ lib.tcl_adam_step.restype = C.c_int
 
 lib.tcl_debug_attention_variant.argtypes = [C.c_int]
 lib.tcl_debug_attention_variant.restype = C.c_int
+lib.tcl_debug_attention_trim.argtypes = [C.c_int]
+lib.tcl_debug_attention_trim.restype = C.c_int
 lib.tcl_ddim_next.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float,
                               C.c_float, C.c_void_p]
 lib.tcl_ddim_next.restype = C.c_int

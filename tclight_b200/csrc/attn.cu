@@ -27,6 +27,9 @@ struct AttnParams {
   int heads, d;        // true head dim
   int kv_batch_div;    // kv batch = q batch / kv_batch_div (cross-attention text broadcast)
   int n_kv_tiles;
+  int qk_steps;        // K = 16 MMA steps of Q K^T that carry live head-dim columns: ceil(d / 16)
+  int n_o;             // live rows of a V^T tile = N of the P V MMA: round_up(d + 1, 16) (row d = denominator)
+  uint32_t idesc_o;    // instruction descriptor of the P V MMA (M = 128, N = n_o)
   float scale_log2;    // log2(e) / sqrt(d)
   void* out;           // [B, tq, heads*d]
   long long out_pitch; // heads*d
@@ -89,33 +92,65 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 
-// TS   : P is handed to the P V MMA through TMEM (tcgen05.st + A-from-TMEM MMA) instead of swizzled smem.
-// POLY : 8-bit mask over every 8 consecutive exponentials: set bits run as FMA-pipe polynomials (poly_exp2)
-//        instead of MUFU.EX2.
-// SPLIT: softmax warpgroups per Q tile.  With 2, each thread owns one row x 64 score columns and the two halves
-//        exchange their row maxima through shared memory: 4 softmax warps per scheduler instead of 2 keep the XU
-//        pipe (MUFU.EX2 + F2FP, the binding pipe) busy while other warps sit in their load / max / store phases.
-template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS, int POLY, int SPLIT, int MINB>
-__global__ void __launch_bounds__(NQ * 128 * SPLIT + 32 + NQ * 32, MINB)
+// Packed-pair variants (Blackwell FFMA2 / FADD2: two fp32 lanes per issue slot).  The FMA pipe does 128 lanes/clk/SM either
+// way (tools/ubench/pipes.cu), but the packed forms halve the issue slots of the scale and polynomial arithmetic, which
+// is what the softmax warps run out of next to MUFU.EX2 (16 lanes/clk/SM).
+template <bool BF16>
+__device__ __forceinline__ float2 poly_exp2_pair(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 t = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));
+  const float2 r = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(r, make_float2(-1.f, -1.f), x);          // x - round(x), exact
+  float2 pl;
+  if (BF16) {
+    pl = __ffma2_rn(make_float2(0.055838283f, 0.055838283f), f, make_float2(0.24263948f, 0.24263948f));
+    pl = __ffma2_rn(pl, f, make_float2(0.69313675f, 0.69313675f));
+    pl = __ffma2_rn(pl, f, make_float2(0.99992454f, 0.99992454f));
+  } else {
+    pl = __ffma2_rn(make_float2(0.009666368f, 0.009666368f), f, make_float2(0.055921976f, 0.055921976f));
+    pl = __ffma2_rn(pl, f, make_float2(0.2402235f, 0.2402235f));
+    pl = __ffma2_rn(pl, f, make_float2(0.693121f, 0.693121f));
+    pl = __ffma2_rn(pl, f, make_float2(1.0f, 1.0f));
+  }
+  return make_float2(__int_as_float(__float_as_int(pl.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(pl.y) + (__float_as_int(t.y) << 23)));
+}
+
+// P is handed to the P V MMA through TMEM (tcgen05.st + A-from-TMEM MMA), never through shared memory.
+// POLY  : 8-bit mask; bit b set = unit b of every 8 consecutive units runs exp2 as an FMA-pipe polynomial instead of
+//         MUFU.EX2.  A unit is one score (PACKED = false) or one pair of adjacent scores (PACKED = true).
+// PACKED: scale-subtract and polynomial arithmetic in packed fp32x2 instructions.
+// STALE : tiles after the first form P against the reference of the previous tile while their own row maximum is reduced
+//         concurrently (the max leaves the dependent chain in front of the exponentials).  The score tile is only
+//         released to the next Q K^T once the maximum is known, so a row whose maximum jumped by more than the
+//         representable headroom re-reads its scores from TMEM and redoes the tile against the new reference.
+// Register budget: with two Q tiles the block is three warpgroups (2 x softmax, 1 x {TMA warp, 2 MMA-issuer warps, 1 idle
+// warp}); after setup the service warpgroup shrinks to 88 registers per thread (setmaxnreg.dec) and the softmax
+// warpgroups grow to 200 (setmaxnreg.inc), which is what lets a whole 128-column score row, its packed P and the
+// temporaries of the overlapped max / exp2 stay in registers (at the 168 the launch bound allows they spill).
+template <int NQ, int REGS>
+constexpr int attn_threads() { return REGS > 0 ? 384 : NQ * 128 + 32 + NQ * 32; }
+
+template <int NQ, int DPAD, int KST, int VST, bool BF16, int POLY, bool PACKED, bool STALE, int MINB, int REGS>
+__global__ void __launch_bounds__(attn_threads<NQ, REGS>(), MINB)
 attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnParams p) {
   using E = Elem<BF16>;
   constexpr int NC = DPAD / 64;                    // 64-wide chunks of the head dim
   constexpr uint32_t QK_TILE = 128 * DPAD * 2;     // one Q or K tile (NC chunk tiles of 16 KB)
-  constexpr uint32_t V_CHUNK = DPAD * 128;         // one 64-kv chunk of V^T: DPAD rows x 128 B
+  constexpr uint32_t V_CHUNK = DPAD * 128;         // one 64-kv chunk of V^T: up to DPAD rows x 128 B (n_o rows are loaded)
   constexpr uint32_t V_TILE = 2 * V_CHUNK;
-  constexpr uint32_t P_TILE = 128 * 128 * 2;       // 2 chunk tiles of 16 KB
   constexpr uint32_t OFF_Q = 0;
   constexpr uint32_t OFF_K = OFF_Q + NQ * QK_TILE;
   constexpr uint32_t OFF_V = OFF_K + KST * QK_TILE;
-  constexpr uint32_t OFF_P = OFF_V + VST * V_TILE;
-  constexpr uint32_t OFF_BAR = OFF_P + (TS ? 0 : NQ * P_TILE);
-  constexpr uint32_t TMEM_P = NQ * (128 + DPAD);      // TS: 64 columns of packed P per Q tile
-  constexpr uint32_t TMEM_NEED = NQ * (128 + DPAD + (TS ? 64 : 0));
+  constexpr uint32_t OFF_BAR = OFF_V + VST * V_TILE;
+  constexpr uint32_t TMEM_P = NQ * (128 + DPAD);      // 64 columns of packed P per Q tile
+  constexpr uint32_t TMEM_NEED = NQ * (128 + DPAD + 64);
   static_assert(TMEM_NEED <= 512, "TMEM budget");
   constexpr uint32_t TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
-  constexpr int SOFT_THREADS = NQ * 128 * SPLIT;
-  constexpr int COLS = 128 / SPLIT;                // score columns per softmax thread
-  static_assert(SPLIT == 1 || (SPLIT == 2 && TS), "column split needs P in TMEM");
+  constexpr int SOFT_THREADS = NQ * 128;
+  // largest jump of a row maximum that P (16-bit) and the fp32 accumulator absorb without the slow path
+  constexpr float STALE_LIMIT = BF16 ? 60.f : 6.f;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -132,7 +167,6 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
   uint64_t* p_empty = p_full + NQ;          // NQ
   uint64_t* o_full = p_empty + NQ;          // NQ
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + NQ);
-  float* xch = reinterpret_cast<float*>(smem + OFF_BAR + 256);      // [2 parity][NQ][SPLIT][128] row maxima (SPLIT == 2)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -151,8 +185,8 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
     for (int i = 0; i < VST; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], NQ); }
     for (int i = 0; i < NQ; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128 * SPLIT);
-      mbar_init(&p_full[i], 128 * SPLIT);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 128);
       mbar_init(&p_empty[i], 1);
       mbar_init(&o_full[i], 1);
     }
@@ -165,9 +199,13 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
   // warp-uniform for the compiler (a plain shared-memory load is treated as divergent)
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
+  if (warp >= SOFT_THREADS / 32) {
+  // the service warpgroup gives registers back (every warp of the warpgroup executes the same setmaxnreg)
+  if constexpr (REGS > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == SOFT_THREADS / 32) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      const uint32_t v_bytes = 2u * (uint32_t)p.n_o * 128u;          // only the n_o live rows of V^T travel
       mbar_arrive_expect_tx(q_full, NQ * QK_TILE);
       for (int q = 0; q < NQ; ++q)
         for (int c = 0; c < NC; ++c)
@@ -185,14 +223,14 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
         {
           const int st = vn % VST;
           mbar_wait(&v_empty[st], ((vn / VST) & 1) ^ 1);
-          mbar_arrive_expect_tx(&v_full[st], V_TILE);
+          mbar_arrive_expect_tx(&v_full[st], v_bytes);
           for (int c = 0; c < 2; ++c)
             tma_load_3d(smem + OFF_V + st * V_TILE + c * V_CHUNK, &tm.vt, &v_full[st], j * 128 + c * 64, 0, kv_bh);
           ++vn;
         }
       }
     }
-  } else if (warp > SOFT_THREADS / 32) {
+  } else if (warp > SOFT_THREADS / 32 && warp <= SOFT_THREADS / 32 + NQ) {
     // ===================== MMA issuers: one converged warp per Q tile =====================
     // All 32 lanes run the control flow (so every operand stays in uniform registers and no per-MMA
     // ELECT/R2UR.BROADCAST waterfall is generated — with a single `if (lane == 0)` issuer that waterfall plus
@@ -200,11 +238,11 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
     // one elected lane issues the tcgen05 instructions.
     const int q = warp - (SOFT_THREADS / 32 + 1);
     constexpr uint32_t idesc_s = umma_idesc_f16(BF16, 128, 128);
-    constexpr uint32_t idesc_o = umma_idesc_f16(BF16, 128, DPAD);
+    const uint32_t idesc_o = p.idesc_o;
+    const int qk_steps = p.qk_steps;
     const uint32_t q_base = smem_u32(smem + OFF_Q) + q * QK_TILE;
     const uint32_t k_base = smem_u32(smem + OFF_K);
     const uint32_t v_base = smem_u32(smem + OFF_V);
-    const uint32_t p_base = smem_u32(smem + OFF_P) + (TS ? 0 : q * P_TILE);
     const uint32_t t_s = tmem_base + q * 128;
     const uint32_t t_o = tmem_base + NQ * 128 + q * DPAD;
     const uint32_t t_p = tmem_base + TMEM_P + q * 64;
@@ -217,12 +255,14 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       TRACE_EV(2, q * 4 + 1, jn);
       tcgen05_fence_after();
       if (elect_one()) {
+        // only the K = 16 steps that carry live head-dim columns (d = 40: 3 of the 4 steps of the 64-wide chunk)
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const uint64_t a = umma_desc_k_sw128(q_base + c * 16384);
           const uint64_t bd = umma_desc_k_sw128(k_base + st * QK_TILE + c * 16384);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(t_s, a + 2 * k, bd + 2 * k, idesc_s, (c | k) != 0);
+          for (int k = 0; k < 4; ++k)
+            if (c * 4 + k < qk_steps) umma_f16_ss(t_s, a + 2 * k, bd + 2 * k, idesc_s, (c | k) != 0);
         }
         umma_commit(&s_full[q]);
         umma_commit(&k_empty[st]);       // k_empty counts NQ commits
@@ -252,17 +292,12 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       TRACE_EV(2, q * 4 + 3, j);
       tcgen05_fence_after();
       if (elect_one()) {
+        // N = n_o (d + 1 rounded up to 16): the zero-padded rows of V^T are neither loaded nor multiplied
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const uint64_t bd = umma_desc_k_sw128(v_base + st * V_TILE + c * V_CHUNK);
-          if (TS) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_ts(t_o, t_p + (c * 4 + k) * 8, bd + 2 * k, idesc_o, (j | c | k) != 0);
-          } else {
-            const uint64_t a = umma_desc_k_sw128(p_base + c * 16384);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_ss(t_o, a + 2 * k, bd + 2 * k, idesc_o, (j | c | k) != 0);
-          }
+          for (int k = 0; k < 4; ++k) umma_f16_ts(t_o, t_p + (c * 4 + k) * 8, bd + 2 * k, idesc_o, (j | c | k) != 0);
         }
         umma_commit(&p_empty[q]);
         umma_commit(&v_empty[st]);       // v_empty counts NQ commits
@@ -270,18 +305,57 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       }
       __syncwarp();
     }
+  }
   } else {
     // ===================== softmax warpgroups =====================
-    const int q = warp / (4 * SPLIT);        // which Q tile
-    const int half = (warp >> 2) % SPLIT;    // which column range of the score tile
+    if constexpr (REGS > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
+    const int q = warp >> 2;                 // which Q tile
     const int row = (warp & 3) * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const uint32_t t_s = t_lane + q * 128 + half * COLS;
+    const uint32_t t_s = t_lane + q * 128;
     const uint32_t t_o = t_lane + NQ * 128 + q * DPAD;
+    const uint32_t t_p = t_lane + TMEM_P + q * 64;
     float m_ref = -INFINITY;                 // reference max (scaled, log2 domain) used by exp2
-    const uint32_t p_tile_addr = smem_u32(smem + OFF_P + (TS ? 0 : q * P_TILE));
-    const uint32_t t_p = t_lane + TMEM_P + q * 64 + half * (COLS / 2);
-    const bool tracer = threadIdx.x == q * 128 * SPLIT;
+    float pend = 1.f;                        // STALE: factor owed to O from the previous tile's maximum
+    const bool tracer = threadIdx.x == q * 128;
+    const float sc = p.scale_log2;
+
+    // exp2(s * scale - ref) of 32 scores -> 16 packed 16-bit pairs
+    auto exp_chunk = [&](const uint32_t (&s)[32], uint32_t* pk, float ref) {
+      if constexpr (PACKED) {
+        const float2 sc2 = make_float2(sc, sc), nref2 = make_float2(-ref, -ref);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float2 a = __ffma2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, nref2);
+          float2 e;
+          if ((POLY >> ((i >> 1) & 7)) & 1) e = poly_exp2_pair<BF16>(a);
+          else e = make_float2(fast_exp2(a.x), fast_exp2(a.y));
+          pk[i >> 1] = E::pack(e.x, e.y);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float a0 = fmaf(__uint_as_float(s[i]), sc, -ref);
+          const float a1 = fmaf(__uint_as_float(s[i + 1]), sc, -ref);
+          const float e0 = ((POLY >> (i & 7)) & 1) ? poly_exp2<BF16>(a0) : fast_exp2(a0);
+          const float e1 = ((POLY >> ((i + 1) & 7)) & 1) ? poly_exp2<BF16>(a1) : fast_exp2(a1);
+          pk[i >> 1] = E::pack(e0, e1);
+        }
+      }
+    };
+    auto max_chunk = [&](const uint32_t (&s)[32], float& a, float& bq) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        a = fmaxf(a, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+        bq = fmaxf(bq, fmaxf(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])));
+      }
+    };
+    auto mask_chunk = [&](uint32_t (&s)[32], int c0, int valid_cols) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c0 + i >= valid_cols) s[i] = 0xff800000u;   // -inf
+    };
+
     // A barrier probe costs ~250 clk even when the phase is long complete (measured with the clock64 trace), so
     // both per-tile barriers are probed early with the non-blocking form and the result is consumed later: the
     // blocking wait only runs when the early probe failed.
@@ -294,77 +368,65 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       uint32_t s0[32], s1[32], s2[32], s3[32];
       tmem_ld_32x32b_x32(t_s + 0, s0);
       tmem_ld_32x32b_x32(t_s + 32, s1);
-      if constexpr (SPLIT == 1) {
-        tmem_ld_32x32b_x32(t_s + 64, s2);
-        tmem_ld_32x32b_x32(t_s + 96, s3);
-      }
+      tmem_ld_32x32b_x32(t_s + 64, s2);
+      tmem_ld_32x32b_x32(t_s + 96, s3);
       const bool pe_ready = mbar_test_wait(&p_empty[q], (j & 1) ^ 1);   // P V of the previous tile: consumed after the exps
       tmem_ld_wait();
-      tcgen05_fence_before();
-      mbar_arrive(&s_empty[q]);
-      if (tracer) TRACE_EV(q, 2, j);
-      const int valid_cols = p.tk - j * 128 - half * COLS;
-      const bool tail = valid_cols < COLS;      // warp-uniform: only the last KV tile
-      if (tail) {
-        auto mask = [&](uint32_t (&s)[32], int c0) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i >= valid_cols) s[i] = 0xff800000u;   // -inf
-        };
-        mask(s0, 0); mask(s1, 32);
-        if constexpr (SPLIT == 1) { mask(s2, 64); mask(s3, 96); }
-      }
-      // independent max chains (a single 128-long dependent chain costs ~500 clk)
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 32; i += SPLIT) {
-        if constexpr (SPLIT == 1) {
-          mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
-          mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
-          mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
-        } else {
-          mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(s0[i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(s1[i]));
-          mx3 = fmaxf(mx3, __uint_as_float(s1[i + 1]));
-        }
-      }
-      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      if constexpr (SPLIT == 2) {
-        // row maximum over both column halves: exchange through shared memory (double-buffered by tile parity; the
-        // named barrier of tile j+1 orders every read of tile j before any write of tile j+2)
-        float* slot = xch + (((j & 1) * NQ + q) * SPLIT) * 128;
-        slot[half * 128 + row] = mx;
-        asm volatile("bar.sync %0, 256;" ::"r"(1 + q) : "memory");
-        mx = fmaxf(mx, slot[(half ^ 1) * 128 + row]);
-      }
-      const float m_new = mx * p.scale_log2;
+      const int valid_cols = p.tk - j * 128;
+      const bool tail = valid_cols < 128;      // warp-uniform: only the last KV tile
+      if (tail) { mask_chunk(s0, 0, valid_cols); mask_chunk(s1, 32, valid_cols); mask_chunk(s2, 64, valid_cols); mask_chunk(s3, 96, valid_cols); }
+      uint32_t pk[64];
       float factor = 1.f;
-      if (j == 0) {
-        m_ref = m_new;
-      } else if (m_new > m_ref + 8.f) {
-        factor = fast_exp2(m_ref - m_new);
-        m_ref = m_new;
-      }
-      // 3 of every 8 exponentials run as polynomials on the FMA pipe, 5 on MUFU.EX2 (16 lanes/clk/SM is the
-      // binding pipe of this kernel; the split balances the two pipes)
-      uint32_t pk[COLS / 2];
-      auto do_chunk = [&](uint32_t (&s)[32], int c0) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float a0 = fmaf(__uint_as_float(s[i]), p.scale_log2, -m_ref);
-          const float a1 = fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_ref);
-          const float e0 = ((POLY >> (i & 7)) & 1) ? poly_exp2<BF16>(a0) : fast_exp2(a0);
-          const float e1 = ((POLY >> ((i + 1) & 7)) & 1) ? poly_exp2<BF16>(a1) : fast_exp2(a1);
-          pk[(c0 + i) >> 1] = E::pack(e0, e1);
+      if (!STALE || j == 0) {
+        // exact reference: row maximum first (independent chains: one 128-long dependent chain costs ~500 clk)
+        tcgen05_fence_before();
+        mbar_arrive(&s_empty[q]);
+        if (tracer) TRACE_EV(q, 2, j);
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        max_chunk(s0, mx0, mx1); max_chunk(s1, mx2, mx3); max_chunk(s2, mx0, mx1); max_chunk(s3, mx2, mx3);
+        const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+        if (j == 0) {
+          m_ref = m_new;
+        } else if (m_new > m_ref + 8.f) {
+          factor = fast_exp2(m_ref - m_new);
+          m_ref = m_new;
         }
-      };
-      do_chunk(s0, 0);
-      do_chunk(s1, 32);
-      if constexpr (SPLIT == 1) {
-        do_chunk(s2, 64);
-        do_chunk(s3, 96);
+        exp_chunk(s0, pk + 0, m_ref);
+        exp_chunk(s1, pk + 16, m_ref);
+        exp_chunk(s2, pk + 32, m_ref);
+        exp_chunk(s3, pk + 48, m_ref);
+      } else {
+        // stale reference: the first quarter of the exponentials runs next to the max reduction of the whole tile
+        factor = pend;
+        pend = 1.f;
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        max_chunk(s0, mx0, mx1); max_chunk(s1, mx2, mx3); max_chunk(s2, mx0, mx1); max_chunk(s3, mx2, mx3);
+        exp_chunk(s0, pk + 0, m_ref);
+        const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+        float m_next = m_ref;
+        if (__any_sync(0xffffffffu, m_new > m_ref + STALE_LIMIT)) {
+          // rare: this tile would overflow against the old reference -> move the reference NOW (O is rescaled before
+          // this tile's P V) and redo the first quarter from the scores still held in TMEM
+          if (m_new > m_ref + 8.f) {
+            factor *= fast_exp2(m_ref - m_new);
+            m_ref = m_new;
+            m_next = m_new;
+          }
+          tmem_ld_32x32b_x32(t_s + 0, s0);
+          tmem_ld_wait();
+          if (tail) mask_chunk(s0, 0, valid_cols);
+          exp_chunk(s0, pk + 0, m_ref);
+        } else if (m_new > m_ref + 8.f) {
+          pend = fast_exp2(m_ref - m_new);     // applied to O before the NEXT tile's P V
+          m_next = m_new;
+        }
+        tcgen05_fence_before();
+        mbar_arrive(&s_empty[q]);
+        if (tracer) TRACE_EV(q, 2, j);
+        exp_chunk(s1, pk + 16, m_ref);
+        exp_chunk(s2, pk + 32, m_ref);
+        exp_chunk(s3, pk + 48, m_ref);
+        m_ref = m_next;
       }
       // the previous P V MMA must be done before P or O are touched.  Waiting here (not before the exponentials)
       // gives it the whole softmax of this tile to complete: the ncu source view of the earlier placement showed
@@ -376,39 +438,23 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       if (__any_sync(0xffffffffu, factor != 1.f)) {
         tcgen05_fence_after();
 #pragma unroll 1
-        for (int c0 = half * (DPAD / SPLIT); c0 < (half + 1) * (DPAD / SPLIT); c0 += 32) {
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(t_o + c0, o);
+        for (int c0 = 0; c0 < p.n_o; c0 += 16) {
+          uint32_t o[16];
+          tmem_ld_32x32b_x16(t_o + c0, o);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-          tmem_st_32x32b_x32(t_o + c0, o);
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+          tmem_st_32x32b_x16(t_o + c0, o);
         }
         tmem_st_wait();
       }
-      if (TS) {
-        // P -> TMEM: lane = row, 32-bit column c holds keys (2c, 2c+1) — the K-major A operand of the P V MMA
+      // P -> TMEM: lane = row, 32-bit column c holds keys (2c, 2c+1) — the K-major A operand of the P V MMA
+      {
         uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[0]);
+        uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
         tmem_st_32x32b_x32(t_p, lo);
-        if constexpr (SPLIT == 1) {
-          uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
-          tmem_st_32x32b_x32(t_p + 32, hi);
-        }
+        tmem_st_32x32b_x32(t_p + 32, hi);
         tmem_st_wait();
-      } else {
-#pragma unroll
-        for (int c = 0; c < 2 / SPLIT; ++c) {
-          const uint32_t rowa = p_tile_addr + c * 16384 + row * 128;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int pu = u ^ (row & 7);
-            // explicit st.shared.v4: a generic-pointer store compiles to ST.E + splits into 32/64-bit pieces
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + pu * 16), "r"(pk[c * 32 + u * 4 + 0]),
-                         "r"(pk[c * 32 + u * 4 + 1]), "r"(pk[c * 32 + u * 4 + 2]), "r"(pk[c * 32 + u * 4 + 3])
-                         : "memory");
-          }
-        }
-        fence_proxy_async_smem();
       }
       tcgen05_fence_before();
       mbar_arrive(&p_full[q]);
@@ -427,12 +473,12 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
 #pragma unroll
       for (int i = 0; i < 16; ++i)
         if (i == (p.d & 15)) l = __uint_as_float(v[i]);
-      inv_l = 1.0f / l;
+      inv_l = 1.0f / l;        // (a factor still owed to O after the last tile cancels in O / l)
     }
     typename E::T* out = reinterpret_cast<typename E::T*>(p.out) +
                          (static_cast<long long>(b) * p.tq + t) * p.out_pitch + head * p.d;
 #pragma unroll 1
-    for (int c0 = half * 16; c0 < p.d; c0 += 16 * SPLIT) {     // the column halves share the output chunks
+    for (int c0 = 0; c0 < p.d; c0 += 16) {
       uint32_t v[16];
       tmem_ld_32x32b_x16(t_o + c0, v);
       tmem_ld_wait();
@@ -455,13 +501,12 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
   }
 }
 
-template <int NQ, int DPAD, int KST, int VST, bool BF16, bool TS = false, int POLY = 0, int SPLIT = 1, int MINB = 1>
+template <int NQ, int DPAD, int KST, int VST, bool BF16, int POLY, bool PACKED, bool STALE, int MINB = 1, int REGS = 0>
 static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, int bh, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)NQ * 128 * DPAD * 2 + (size_t)KST * 128 * DPAD * 2 +
-                          (size_t)VST * 2 * DPAD * 128 + (TS ? 0 : (size_t)NQ * 128 * 128 * 2) + 1024 + 256 + 4096;
+  constexpr size_t smem = (size_t)NQ * 128 * DPAD * 2 + (size_t)KST * 128 * DPAD * 2 + (size_t)VST * 2 * DPAD * 128 + 1024 + 256;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, SPLIT, MINB>,
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NQ, DPAD, KST, VST, BF16, POLY, PACKED, STALE, MINB, REGS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_last_error("attention: cudaFuncSetAttribute(%zu B) failed: %s", smem, cudaGetErrorString(e));
@@ -470,7 +515,8 @@ static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, in
     configured = true;
   }
   dim3 grid((q_tiles + NQ - 1) / NQ, bh);
-  attn_kernel<NQ, DPAD, KST, VST, BF16, TS, POLY, SPLIT, MINB><<<grid, NQ * 128 * SPLIT + 32 + NQ * 32, smem, stream>>>(tm, p);
+  static_assert(REGS == 0 || (NQ == 2 && REGS % 8 == 0 && (4 * 88 + 8 * REGS) * 32 <= 65536), "register split");
+  attn_kernel<NQ, DPAD, KST, VST, BF16, POLY, PACKED, STALE, MINB, REGS><<<grid, attn_threads<NQ, REGS>(), smem, stream>>>(tm, p);
   TCL_CHECK_LAUNCH("tcl_attention");
   return TCL_OK;
 }
@@ -479,7 +525,8 @@ static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, in
 
 using namespace tcl;
 
-static int g_attn_variant = 2;   // P through TMEM + 2 of 8 exponentials on the FMA pipe (fastest measured, profiles/r01_attention_v2_variants.txt)
+static int g_attn_variant = -1;  // -1 = shipped configuration; >= 0 selects a tuning variant (tools/bench_attn_variants.py)
+static int g_attn_trim = 1;      // 0 = issue the full padded MMA shapes (tuning reference)
 static long long* g_attn_trace = nullptr;
 
 extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
@@ -494,6 +541,17 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
   const bool bf16 = a->dtype == TCL_DTYPE_BF16;
   const int bh = a->batch * a->heads;
   const int kv_bh = (a->batch / a->kv_batch_div) * a->heads;
+  AttnParams p;
+  p.tq = a->tq; p.tk = a->tk; p.heads = a->heads; p.d = a->d;
+  p.kv_batch_div = a->kv_batch_div;
+  p.n_kv_tiles = (a->tk + 127) / 128;
+  p.qk_steps = g_attn_trim ? (a->d + 15) / 16 : a->d_pad / 16;
+  p.n_o = g_attn_trim ? (a->d + 1 + 15) / 16 * 16 : a->d_pad;
+  p.idesc_o = umma_idesc_f16(bf16, 128, (uint32_t)p.n_o);
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)a->d);
+  p.out = a->out;
+  p.out_pitch = (long long)a->heads * a->d;
+  p.trace = g_attn_trace;
   AttnTmaps tm;
   {
     const uint64_t dims[3] = {(uint64_t)a->d_pad, (uint64_t)a->tq, (uint64_t)bh};
@@ -512,69 +570,57 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
   {
     const uint64_t dims[3] = {(uint64_t)a->tk, (uint64_t)a->d_pad, (uint64_t)kv_bh};
     const uint64_t str[2] = {(uint64_t)a->tk_pitch * 2, (uint64_t)a->d_pad * a->tk_pitch * 2};
-    const uint32_t box[3] = {64, (uint32_t)a->d_pad, 1}, es[3] = {1, 1, 1};
+    const uint32_t box[3] = {64, (uint32_t)p.n_o, 1}, es[3] = {1, 1, 1};      // only the live rows of V^T
     int rc = make_tmap(&tm.vt, a->vt, bf16, 3, dims, str, box, es, 128);
     if (rc) return rc;
   }
-  AttnParams p;
-  p.tq = a->tq; p.tk = a->tk; p.heads = a->heads; p.d = a->d;
-  p.kv_batch_div = a->kv_batch_div;
-  p.n_kv_tiles = (a->tk + 127) / 128;
-  p.scale_log2 = 1.4426950408889634f / sqrtf((float)a->d);
-  p.out = a->out;
-  p.out_pitch = (long long)a->heads * a->d;
-  p.trace = g_attn_trace;
   const int q_tiles = (a->tq + 127) / 128;
   const int var = g_attn_variant;
   if (a->d_pad == 64) {
     // short key sequences (cross-attention on the 77 / 154 text tokens): the per-CTA latency chain (TMEM alloc, Q / K / V
     // loads, two serial tiles, epilogue) dominates, so run one Q tile per CTA and two CTAs per SM (256 TMEM columns,
     // 85 KB of shared memory each) to overlap the chains of neighbouring tiles
-    if (var >= 1 && var != 8 && a->tk <= 256) {
-      return bf16 ? launch_attn<1, 64, 2, 2, true, true, 0x03, 1, 2>(tm, p, q_tiles, bh, stream)
-                  : launch_attn<1, 64, 2, 2, false, true, 0x00, 1, 2>(tm, p, q_tiles, bh, stream);
+    if (a->tk <= 256) {
+      return bf16 ? launch_attn<1, 64, 2, 2, true, 0x11, true, false, 2>(tm, p, q_tiles, bh, stream)
+                  : launch_attn<1, 64, 2, 2, false, 0x00, true, false, 2>(tm, p, q_tiles, bh, stream);
     }
+    // long key sequences (merged self-attention): two Q tiles per CTA, packed-pair arithmetic, 2 of every 8 pairs of
+    // exponentials on the FMA pipe, 200 registers per softmax thread (measured sweep: profiles/r02_attention_variants.txt)
     if (!bf16) {
-      if (var >= 3) return launch_attn<2, 64, 4, 3, false, true, 0, 2>(tm, p, q_tiles, bh, stream);
-      return var >= 1 ? launch_attn<2, 64, 4, 3, false, true>(tm, p, q_tiles, bh, stream)
-                      : launch_attn<2, 64, 3, 2, false>(tm, p, q_tiles, bh, stream);
+      switch (var) {
+        case 0: return launch_attn<2, 64, 4, 3, false, 0x00, false, false>(tm, p, q_tiles, bh, stream);
+        case 8: return launch_attn<2, 64, 4, 3, false, 0x11, true, true, 1, 200>(tm, p, q_tiles, bh, stream);
+        default: return launch_attn<2, 64, 4, 3, false, 0x11, true, false, 1, 200>(tm, p, q_tiles, bh, stream);
+      }
     }
     switch (var) {
-      case 1: return launch_attn<2, 64, 4, 3, true, true, 0x00>(tm, p, q_tiles, bh, stream);
-      case 2: case 8: return launch_attn<2, 64, 4, 3, true, true, 0x03>(tm, p, q_tiles, bh, stream);
-      case 3: return launch_attn<2, 64, 4, 3, true, true, 0x00, 2>(tm, p, q_tiles, bh, stream);
-      case 4: return launch_attn<2, 64, 4, 3, true, true, 0x03, 2>(tm, p, q_tiles, bh, stream);
-      case 5: return launch_attn<2, 64, 4, 3, true, true, 0x13, 2>(tm, p, q_tiles, bh, stream);
-      case 6: return launch_attn<2, 64, 4, 3, true, true, 0x33, 2>(tm, p, q_tiles, bh, stream);
-      case 7: return launch_attn<2, 64, 4, 3, true, true, 0x11, 2>(tm, p, q_tiles, bh, stream);
-      default: return launch_attn<2, 64, 3, 2, true>(tm, p, q_tiles, bh, stream);
+      case 0: return launch_attn<2, 64, 4, 3, true, 0x03, false, false>(tm, p, q_tiles, bh, stream);
+      case 5: return launch_attn<2, 64, 4, 3, true, 0x49, true, false, 1, 200>(tm, p, q_tiles, bh, stream);
+      case 8: return launch_attn<2, 64, 4, 3, true, 0x11, true, true, 1, 200>(tm, p, q_tiles, bh, stream);
+      default: return launch_attn<2, 64, 4, 3, true, 0x11, true, false, 1, 200>(tm, p, q_tiles, bh, stream);
     }
   } else if (a->d_pad == 128) {
-    if (var >= 3)
-      return bf16 ? launch_attn<1, 128, 3, 2, true, true, 0, 2>(tm, p, q_tiles, bh, stream)
-                  : launch_attn<1, 128, 3, 2, false, true, 0, 2>(tm, p, q_tiles, bh, stream);
-    if (var >= 1)
-      return bf16 ? launch_attn<1, 128, 3, 2, true, true>(tm, p, q_tiles, bh, stream)
-                  : launch_attn<1, 128, 3, 2, false, true>(tm, p, q_tiles, bh, stream);
-    return bf16 ? launch_attn<1, 128, 2, 2, true>(tm, p, q_tiles, bh, stream)
-                : launch_attn<1, 128, 2, 2, false>(tm, p, q_tiles, bh, stream);
+    // one Q tile per CTA (TMEM: 128 S + 128 O + 64 P): registers are plentiful, the stale-reference softmax wins (+8 %)
+    if (var == 0)
+      return bf16 ? launch_attn<1, 128, 3, 2, true, 0, false, false>(tm, p, q_tiles, bh, stream)
+                  : launch_attn<1, 128, 3, 2, false, 0, false, false>(tm, p, q_tiles, bh, stream);
+    return bf16 ? launch_attn<1, 128, 3, 2, true, 0x11, true, true>(tm, p, q_tiles, bh, stream)
+                : launch_attn<1, 128, 3, 2, false, 0x00, true, true>(tm, p, q_tiles, bh, stream);
   } else {
-    if (var >= 3)
-      return bf16 ? launch_attn<1, 192, 2, 1, true, true, 0, 2>(tm, p, q_tiles, bh, stream)
-                  : launch_attn<1, 192, 2, 1, false, true, 0, 2>(tm, p, q_tiles, bh, stream);
-    if (var >= 1)
-      return bf16 ? launch_attn<1, 192, 2, 1, true, true>(tm, p, q_tiles, bh, stream)
-                  : launch_attn<1, 192, 2, 1, false, true>(tm, p, q_tiles, bh, stream);
-    return bf16 ? launch_attn<1, 192, 2, 1, true>(tm, p, q_tiles, bh, stream)
-                : launch_attn<1, 192, 2, 1, false>(tm, p, q_tiles, bh, stream);
+    return bf16 ? launch_attn<1, 192, 2, 1, true, 0x00, true, false>(tm, p, q_tiles, bh, stream)
+                : launch_attn<1, 192, 2, 1, false, 0x00, true, false>(tm, p, q_tiles, bh, stream);
   }
 }
 
-// Tuning hook: selects the kernel variant used by tcl_attention (0 = P through shared memory; 1.. = P through
-// TMEM with different exp2 shares / column-split softmax, see the dispatch above).  Returns the previous value.
+// Tuning hooks (tools/bench_attn_variants.py): kernel variant (-1 = shipped) and MMA-shape trimming; return the previous value.
 extern "C" int tcl_debug_attention_variant(int v) {
   const int old = g_attn_variant;
   g_attn_variant = v;
+  return old;
+}
+extern "C" int tcl_debug_attention_trim(int on) {
+  const int old = g_attn_trim;
+  g_attn_trim = on;
   return old;
 }
 
