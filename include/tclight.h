@@ -269,18 +269,51 @@ int tcl_uvt_iteration(const tcl_postopt_ctx* ctx, const int* idx_host, int n_bat
 int tcl_exposure_iteration(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, float* exposure, float* grad,
                            float* m, float* v, float lr, float beta1, float beta2, float eps, int step,
                            float* loss_out, tcl_stream_t stream);
-/* Data-parallel split of the two calls above (each rank takes a slice of the batch, the
- * [U,3] / [N,12] gradients are all-reduced, every rank applies the same Adam step): gradient accumulation
- * only (loss_out = this rank's additive share of {loss, flow, photometric}), then tcl_adam_step. */
-int tcl_uvt_gradient(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, const int* ids, long long U,
-                     const float* fdc, float* grad, float* loss_out, tcl_stream_t stream);
+/* Data-parallel split (each rank takes a slice of the batch; loss_out = this rank's additive share
+ * of {loss, flow, photometric}; ctx.norm_batch / norm_valid carry the GLOBAL normalisers).
+ *
+ * Stage 1: tcl_exposure_gradient -> all-reduce of the [N,12] gradient (1.2 KB/frame) -> tcl_adam_step on every rank.
+ *
+ * Stage 2: the UVT rows and their gradient are SHARDED by row range over the ranks of one NVSwitch box, and every
+ * shard is mapped into every rank's address space (CUDA IPC, tcl_ipc_open).  tcl_uvt_gradient_sharded gathers rows
+ * with plain (peer) loads and scatters gradients with 16-byte (peer) reductions from inside the gather / level-0
+ * kernels, so only the rows a batch touches cross NVLink; after a cross-rank barrier each rank runs
+ * tcl_adam_step_uvt on ITS shard (dense Adam, 1/world of the rows), and a second barrier orders it before the next
+ * gather.  Row id -> (owner = id / rows_per_rank, local = id % rows_per_rank).  No dense all-reduce, no replicated
+ * Adam.  Replaces the autograd index_select / index_add_ + optimizer.step of generate.py:496-517. */
+#define TCL_MAX_RANKS 8
+typedef struct {
+  int32_t world, rank;
+  int64_t rows_per_rank;        /* ceil(U / world) rounded up to a multiple of 4 (>= 256 when world > 1)        */
+  float* fdc[TCL_MAX_RANKS];    /* shard r: [rows_per_rank,3]; entry `rank` is local, the others peer mappings   */
+  float* grad[TCL_MAX_RANKS];   /* shard r: [rows_per_rank,4], zero-filled once by its owner                     */
+} tcl_uvt_shards;
+int tcl_uvt_gradient_sharded(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, const int* ids,
+                             const tcl_uvt_shards* shards, float* loss_out, tcl_stream_t stream);
 int tcl_exposure_gradient(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, const float* exposure, float* grad,
                           float* loss_out, tcl_stream_t stream);
 int tcl_adam_step(float* p, float* grad, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                   int step, tcl_stream_t stream);
-/* the same for the UVT rows: fdc, m, v are [U,3], grad4 is the [U,4] gradient of tcl_uvt_gradient */
-int tcl_adam_step_uvt(float* fdc, float* grad4, float* m, float* v, long long U, float lr, float beta1, float beta2,
+/* Adam over a UVT row shard: fdc, m, v are [rows,3], grad4 the [rows,4] gradient; leaves the gradient zeroed */
+int tcl_adam_step_uvt(float* fdc, float* grad4, float* m, float* v, long long rows, float lr, float beta1, float beta2,
                       float eps, int step, tcl_stream_t stream);
+/* Shard storage: tcl_peer_alloc = cudaMalloc of its own (outside any caching allocator), zero-filled, plus the
+ * 64-byte cudaIpcMemHandle_t of its base in handle_out; the owner frees it with tcl_peer_free after every peer
+ * has unmapped it.  tcl_ipc_open maps a peer's handle (same box) into this process: *base receives the mapped
+ * address; handles are cached per process (opening one twice returns the same mapping); tcl_ipc_close_all unmaps
+ * them all, tcl_ipc_close one. */
+int tcl_peer_alloc(size_t bytes, void** ptr, void* handle_out);
+int tcl_peer_free(void* ptr);
+int tcl_ipc_open(const void* handle, void** base);
+int tcl_ipc_close(void* base);
+int tcl_ipc_close_all(void);
+/* Cross-rank barrier on the stream, over peer-mapped flags: flags[r] = rank r's int32[TCL_MAX_RANKS] slot array
+ * (zero-filled once).  Rank `rank` adds 1 to slot `rank` of every peer (release, system scope) and waits until all
+ * its own slots reach `epoch` (acquire); `epoch` is 1 for the first barrier and grows by 1 per call.  Work enqueued
+ * after the call sees every peer's writes enqueued before their matching call.  Gives up (and flags the error in
+ * tcl_peer_barrier_timeouts) after ~2 s instead of hanging the device. */
+int tcl_peer_barrier(int32_t* const* flags, int world, int rank, int epoch, tcl_stream_t stream);
+long long tcl_peer_barrier_timeouts(void);
 /* generate.py:477-479: fdc = RGB2SH(scatter_mean(edited, unq_inv)); cnt_ws = U floats of scratch */
 int tcl_uvt_init(const float* edited, const int* ids, int N, int H, int W, long long U, float* fdc, float* cnt_ws,
                  tcl_stream_t stream);
@@ -319,11 +352,6 @@ int tcl_flow_ids(const float* frames, const float* flows, const float* mask_bwds
 size_t tcl_unique_inverse_workspace_bytes(long long id_range);
 int tcl_unique_inverse(const int* ids, long long n, long long id_range, long long* inverse, long long* num_unique,
                        void* workspace, size_t workspace_bytes, tcl_stream_t stream);
-
-/* test hook: one relaxed-SSIM level (utils/loss_utils.py:73-123) forward sums and/or backward
- * of sum_p coef[p]*sum(map_p) for X, Y = [planes, h, w]; planes % 3 == 0. */
-int tcl_debug_ssim_level(const float* X, const float* Y, int planes, int h, int w, const float* coef, int use_ssim,
-                         float* sums, float* dX, tcl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -233,13 +233,34 @@ lib.tcl_uvt_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int
 lib.tcl_uvt_render.restype = C.c_int
 lib.tcl_exposure_bake.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
 lib.tcl_exposure_bake.restype = C.c_int
-lib.tcl_debug_ssim_level.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
-                                     C.c_void_p, C.c_void_p]
-lib.tcl_debug_ssim_level.restype = C.c_int
 
-lib.tcl_uvt_gradient.argtypes = [C.POINTER(PostoptCtx), C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,
-                                 C.c_void_p, C.c_void_p, C.c_void_p]
-lib.tcl_uvt_gradient.restype = C.c_int
+TCL_MAX_RANKS = 8
+
+
+class UvtShards(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32), ("rows_per_rank", C.c_int64),
+        ("fdc", C.c_void_p * TCL_MAX_RANKS), ("grad", C.c_void_p * TCL_MAX_RANKS),
+    ]
+
+
+lib.tcl_uvt_gradient_sharded.argtypes = [C.POINTER(PostoptCtx), C.POINTER(C.c_int), C.c_int, C.c_void_p, C.POINTER(UvtShards),
+                                         C.c_void_p, C.c_void_p]
+lib.tcl_uvt_gradient_sharded.restype = C.c_int
+lib.tcl_peer_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+lib.tcl_peer_alloc.restype = C.c_int
+lib.tcl_peer_free.argtypes = [C.c_void_p]
+lib.tcl_peer_free.restype = C.c_int
+lib.tcl_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+lib.tcl_ipc_open.restype = C.c_int
+lib.tcl_ipc_close.argtypes = [C.c_void_p]
+lib.tcl_ipc_close.restype = C.c_int
+lib.tcl_ipc_close_all.argtypes = []
+lib.tcl_ipc_close_all.restype = C.c_int
+lib.tcl_peer_barrier.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p]
+lib.tcl_peer_barrier.restype = C.c_int
+lib.tcl_peer_barrier_timeouts.argtypes = []
+lib.tcl_peer_barrier_timeouts.restype = C.c_longlong
 lib.tcl_exposure_gradient.argtypes = [C.POINTER(PostoptCtx), C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p]
 lib.tcl_exposure_gradient.restype = C.c_int

@@ -73,67 +73,161 @@ __global__ void avgpool2_kernel(const float* __restrict__ in, long long in_strid
 }
 
 // ------------------------------------------------------------------------------------------
-// SSIM forward at one pyramid level: per plane sums of cs_map and ssim_map over the valid region.
-// X planes: [Bo*3] batch-local; Y planes: frame-indexed pyramid of the target video.
+// Relaxed-SSIM kernels over ALL pyramid levels 1..4 in one launch each (utils/loss_utils.py:73-123, the 11-tap
+// sigma-1.5 valid separable Gaussian of pytorch_msssim: vertical pass first, then horizontal).
+//   ssim_fwd_all : per (level, plane) sums of the cs / ssim maps, and the per-position partial derivatives
+//                  d(map)/d(mu1, E[x^2], E[xy]) (un-scaled: the per-plane loss coefficient is only known once every
+//                  level's mean exists, because MS-SSIM is a product over levels), stored for the backward pass.
+//   ssim_bwd_all : own_l = coef * (G^T dmu1 + 2 x G^T de11 + y G^T de12): the gradient each level contributes to
+//                  its own image; the avg-pool backward chain 0.25^k is summed where level 0 is consumed.
+// Both filters run as register strips: a thread produces 8 vertically (4 horizontally) adjacent outputs from 18 (14)
+// shared-memory reads instead of 11 reads per output.
 // ------------------------------------------------------------------------------------------
 constexpr int ST = 32;          // output tile
 constexpr int SR = ST + 10;     // input tile
+constexpr int SPITCH = SR + 1;  // shared-memory row pitch (odd: the horizontal strips are bank-conflict free)
+
+struct LevelPlan {
+  int h[5], w[5];               // image sizes of levels 1..4 (index = level)
+  long long off[5];             // element offset of level l inside a pyramid plane
+  int tiles_x[5], tiles_y[5];   // tile grid of the launch (map domain for fwd, image domain for bwd)
+  int first[6];                 // first block of level l (first[5] = total)
+  int planes;
+};
 
 struct SsimMaps { float mu1, mu2, e11, e22, e12; };
 
-__device__ __forceinline__ void ssim_point(const SsimMaps& m, float C1, float C2, float& lmap, float& cs) {
-  const float mu1_sq = m.mu1 * m.mu1, mu2_sq = m.mu2 * m.mu2, mu12 = m.mu1 * m.mu2;
-  const float s11 = m.e11 - mu1_sq, s22 = m.e22 - mu2_sq, s12 = m.e12 - mu12;
-  cs = (2.f * s12 + C2) / (s11 + s22 + C2);
-  lmap = (2.f * mu12 + C1) / (mu1_sq + mu2_sq + C1);
+// dst[m][r][c] = sum_k g[k] src[m][r + k][c]   (r < ST, c < SR), strips of 8 rows
+template <int NM, typename F>
+__device__ __forceinline__ void filt_vertical(F load /* (m, row, col) -> float */, float (*dst)[ST][SPITCH]) {
+  for (int t = threadIdx.x; t < NM * 4 * SR; t += blockDim.x) {
+    const int m = t / (4 * SR);
+    const int rem = t - m * 4 * SR;
+    const int strip = rem / SR, cc = rem - strip * SR;
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      const float vin = load(m, strip * 8 + i, cc);
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (i - o >= 0 && i - o < 11) acc[o] += c_gauss[i - o] * vin;
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) dst[m][strip * 8 + o][cc] = acc[o];
+  }
+}
+
+// out[o] = sum_k g[k] src[r][c0 + o + k], o < 4
+__device__ __forceinline__ void filt_row4(const float* src_row, float (&out)[4]) {
+  float in[14];
+#pragma unroll
+  for (int i = 0; i < 14; ++i) in[i] = src_row[i];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) a += c_gauss[k] * in[o + k];
+    out[o] = a;
+  }
+}
+
+__device__ __forceinline__ bool decode_block(const LevelPlan& lp, int& l, int& plane, int& ty0, int& tx0) {
+  const int bid = blockIdx.x;
+  l = 1;
+#pragma unroll
+  for (int i = 2; i <= 4; ++i)
+    if (bid >= lp.first[i]) l = i;
+  const int rem = bid - lp.first[l];
+  const int per = lp.tiles_x[l] * lp.tiles_y[l];
+  plane = rem / per;
+  const int tile = rem - plane * per;
+  ty0 = (tile / lp.tiles_x[l]) * ST;
+  tx0 = (tile - (tile / lp.tiles_x[l]) * lp.tiles_x[l]) * ST;
+  return true;
 }
 
 __global__ void __launch_bounds__(256)
-ssim_fwd_kernel(const float* __restrict__ X, long long x_plane_stride, const float* __restrict__ Y, long long y_frame_stride,
-                long long y_chan_stride, Batch bt, int h, int w, float C1, float C2, float* __restrict__ sums /*[planes][2]*/) {
-  __shared__ float sx[SR][SR + 1], sy[SR][SR + 1];
-  __shared__ float v[5][ST][SR + 1];
+ssim_fwd_all_kernel(const float* __restrict__ X, long long x_plane_stride, const float* __restrict__ Y, long long y_frame_stride,
+                    long long y_chan_stride, Batch bt, LevelPlan lp, float C1, float C2, float* __restrict__ sums /*[4][planes][2]*/,
+                    float* __restrict__ pm /*[planes][3][pyr]*/, long long pm_map_stride) {
+  __shared__ float sxy[2][SR][SPITCH];
+  __shared__ float v[5][ST][SPITCH];
   __shared__ float red[2][8];
-  const int plane = blockIdx.z;           // b*3 + c
+  int l, plane, ty0, tx0;
+  decode_block(lp, l, plane, ty0, tx0);
+  const int h = lp.h[l], w = lp.w[l];
   const int b = plane / 3, c = plane - 3 * b;
-  const float* xp = X + plane * x_plane_stride;
-  const float* yp = Y + bt.idx[b] * y_frame_stride + c * y_chan_stride;
+  const float* xp = X + plane * x_plane_stride + lp.off[l];
+  const float* yp = Y + bt.idx[b] * y_frame_stride + c * y_chan_stride + lp.off[l];
   const int oh = h - 10, ow = w - 10;     // valid map size
-  const int ty0 = blockIdx.y * ST, tx0 = blockIdx.x * ST;
   for (int i = threadIdx.x; i < SR * SR; i += blockDim.x) {
     const int r = i / SR, cc = i - r * SR;
     const int y = ty0 + r, x = tx0 + cc;
     const bool in = y < h && x < w;
-    sx[r][cc] = in ? xp[(long long)y * w + x] : 0.f;
-    sy[r][cc] = in ? yp[(long long)y * w + x] : 0.f;
+    sxy[0][r][cc] = in ? xp[(long long)y * w + x] : 0.f;
+    sxy[1][r][cc] = in ? yp[(long long)y * w + x] : 0.f;
   }
   __syncthreads();
-  // vertical (H) pass first, as pytorch_msssim.gaussian_filter does
-  for (int i = threadIdx.x; i < ST * SR; i += blockDim.x) {
-    const int r = i / SR, cc = i - r * SR;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+  // vertical (H) pass first, as pytorch_msssim.gaussian_filter does: maps x, y, x^2, y^2, xy share their 18 inputs
+  for (int t = threadIdx.x; t < 4 * SR; t += blockDim.x) {
+    const int strip = t / SR, cc = t - strip * SR;
+    float acc[8][5];
 #pragma unroll
-    for (int k = 0; k < 11; ++k) {
-      const float g = c_gauss[k], xv = sx[r + k][cc], yv = sy[r + k][cc];
-      a0 += g * xv; a1 += g * yv; a2 += g * xv * xv; a3 += g * yv * yv; a4 += g * xv * yv;
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+      for (int m = 0; m < 5; ++m) acc[o][m] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      const float xv = sxy[0][strip * 8 + i][cc], yv = sxy[1][strip * 8 + i][cc];
+      const float xx = xv * xv, yy = yv * yv, xy = xv * yv;
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (i - o >= 0 && i - o < 11) {
+          const float g = c_gauss[i - o];
+          acc[o][0] += g * xv; acc[o][1] += g * yv; acc[o][2] += g * xx; acc[o][3] += g * yy; acc[o][4] += g * xy;
+        }
     }
-    v[0][r][cc] = a0; v[1][r][cc] = a1; v[2][r][cc] = a2; v[3][r][cc] = a3; v[4][r][cc] = a4;
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+      for (int m = 0; m < 5; ++m) v[m][strip * 8 + o][cc] = acc[o][m];
   }
   __syncthreads();
   float acc_cs = 0.f, acc_ss = 0.f;
-  for (int i = threadIdx.x; i < ST * ST; i += blockDim.x) {
-    const int r = i / ST, cc = i - r * ST;
-    if (ty0 + r < oh && tx0 + cc < ow) {
-      SsimMaps m = {0.f, 0.f, 0.f, 0.f, 0.f};
+  {
+    const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
+    float f[5][4];
 #pragma unroll
-      for (int k = 0; k < 11; ++k) {
-        const float g = c_gauss[k];
-        m.mu1 += g * v[0][r][cc + k]; m.mu2 += g * v[1][r][cc + k]; m.e11 += g * v[2][r][cc + k];
-        m.e22 += g * v[3][r][cc + k]; m.e12 += g * v[4][r][cc + k];
+    for (int m = 0; m < 5; ++m) filt_row4(&v[m][r][c0], f[m]);
+    const int py_ = ty0 + r;
+    float* pm0 = pm + (long long)plane * 3 * pm_map_stride + lp.off[l] + (long long)py_ * w;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int px_ = tx0 + c0 + o;
+      if (py_ < oh && px_ < ow) {
+        const float mu1 = f[0][o], mu2 = f[1][o], e11 = f[2][o], e22 = f[3][o], e12 = f[4][o];
+        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+        const float A1 = 2.f * mu12 + C1, B1 = mu1_sq + mu2_sq + C1;
+        const float s11 = e11 - mu1_sq, s22 = e22 - mu2_sq, s12 = e12 - mu12;
+        const float A2 = 2.f * s12 + C2, B2 = s11 + s22 + C2;
+        const float cs = A2 / B2;
+        const float lum = A1 / B1;
+        acc_cs += cs; acc_ss += lum * cs;
+        // d cs / d(e12, e11, mu1)
+        const float dcs_e12 = 2.f / B2;
+        const float dcs_e11 = -A2 / (B2 * B2);
+        const float dcs_mu1 = -2.f * mu2 / B2 + 2.f * mu1 * A2 / (B2 * B2);
+        float dmu1, de11, de12;
+        if (l == 4) {           // the coarsest level contributes ssim = l * cs, the others cs only
+          const float dl_mu1 = (2.f * mu2 * B1 - A1 * 2.f * mu1) / (B1 * B1);
+          dmu1 = cs * dl_mu1 + lum * dcs_mu1; de11 = lum * dcs_e11; de12 = lum * dcs_e12;
+        } else {
+          dmu1 = dcs_mu1; de11 = dcs_e11; de12 = dcs_e12;
+        }
+        pm0[px_] = dmu1; pm0[pm_map_stride + px_] = de11; pm0[2 * pm_map_stride + px_] = de12;
       }
-      float l, cs;
-      ssim_point(m, C1, C2, l, cs);
-      acc_cs += cs; acc_ss += l * cs;
     }
   }
   acc_cs = warp_sum(acc_cs); acc_ss = warp_sum(acc_ss);
@@ -142,8 +236,51 @@ ssim_fwd_kernel(const float* __restrict__ X, long long x_plane_stride, const flo
   if (threadIdx.x == 0) {
     float a = 0.f, bsum = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; bsum += red[1][i]; }
-    atomicAdd(&sums[plane * 2 + 0], a);
-    atomicAdd(&sums[plane * 2 + 1], bsum);
+    float* dst = sums + ((size_t)(l - 1) * lp.planes + plane) * 2;
+    atomicAdd(&dst[0], a);
+    atomicAdd(&dst[1], bsum);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ssim_bwd_all_kernel(const float* __restrict__ X, long long x_plane_stride, const float* __restrict__ Y, long long y_frame_stride,
+                    long long y_chan_stride, Batch bt, LevelPlan lp, const float* __restrict__ coef /*[4][planes]*/,
+                    const float* __restrict__ pm, long long pm_map_stride, float* __restrict__ own, long long own_plane_stride) {
+  __shared__ float sp[3][SR][SPITCH];
+  __shared__ float tt[3][ST][SPITCH];
+  int l, plane, qy0, qx0;
+  decode_block(lp, l, plane, qy0, qx0);
+  const int h = lp.h[l], w = lp.w[l];
+  const int b = plane / 3, c = plane - 3 * b;
+  const int oh = h - 10, ow = w - 10;
+  const float* pm0 = pm + (long long)plane * 3 * pm_map_stride + lp.off[l];
+  // map positions [qy0 - 10, qy0 + 31] x [qx0 - 10, qx0 + 31]
+  for (int i = threadIdx.x; i < 3 * SR * SR; i += blockDim.x) {
+    const int m = i / (SR * SR);
+    const int rem = i - m * SR * SR;
+    const int r = rem / SR, cc = rem - r * SR;
+    const int py_ = qy0 - 10 + r, px_ = qx0 - 10 + cc;
+    sp[m][r][cc] = (py_ >= 0 && py_ < oh && px_ >= 0 && px_ < ow) ? pm0[m * pm_map_stride + (long long)py_ * w + px_] : 0.f;
+  }
+  __syncthreads();
+  // transposed filters = the same correlations (the window is symmetric): dX(y) = sum_k g[k] pm(y - k)
+  filt_vertical<3>([&](int m, int r, int cc) { return sp[m][r][cc]; }, tt);
+  __syncthreads();
+  const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
+  const int y = qy0 + r;
+  if (y < h) {
+    float f[3][4];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) filt_row4(&tt[m][r][c0], f[m]);
+    const float g_coef = coef[(size_t)(l - 1) * lp.planes + plane];
+    const float* xp = X + plane * x_plane_stride + lp.off[l] + (long long)y * w;
+    const float* yp = Y + bt.idx[b] * y_frame_stride + c * y_chan_stride + lp.off[l] + (long long)y * w;
+    float* op = own + plane * own_plane_stride + lp.off[l] + (long long)y * w;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int x = qx0 + c0 + o;
+      if (x < w) op[x] = g_coef * (f[0][o] + 2.f * xp[x] * f[1][o] + yp[x] * f[2][o]);
+    }
   }
 }
 
@@ -185,127 +322,82 @@ __global__ void msssim_head_kernel(const float* __restrict__ sums, int planes, P
 }
 
 // ------------------------------------------------------------------------------------------
-// SSIM backward at one level: dX_l = (SSIM term) + avg-pool backward of dX_{l+1}.
-// Output tile BT x BT; recomputes the five filtered maps on the (BT+10)^2 halo.
+// producers of X (batch frames then predecessors)
 // ------------------------------------------------------------------------------------------
-constexpr int BT = 32;
-constexpr int BP = BT + 10;   // partial-map tile
-constexpr int BR = BT + 20;   // input tile
+// UVT rows live in per-rank shards: row id -> (owner rank, local row).  With one rank the table has a
+// single entry.  Every pointer of the table is addressable from this GPU: the local shard, and the peers' shards mapped
+// through CUDA IPC over NVLink, so a gather is a plain (peer) load and a gradient scatter a plain (peer) reduction.
+struct Shards {
+  float* fdc[TCL_MAX_RANKS];      // [rows_per_rank, 3]
+  float* grad[TCL_MAX_RANKS];     // [rows_per_rank, 4]
+  int world;
+  int rows_per_rank;
+  float inv_rows;                 // 1 / rows_per_rank
+};
 
+template <bool W1>
+__device__ __forceinline__ void shard_of(const Shards& sh, int id, int& owner, int& local) {
+  if (W1) { owner = 0; local = id; return; }
+  int o = __float2int_rz(__int2float_rz(id) * sh.inv_rows);
+  int lo = id - o * sh.rows_per_rank;
+  if (lo < 0) { --o; lo += sh.rows_per_rank; }
+  else if (lo >= sh.rows_per_rank) { ++o; lo -= sh.rows_per_rank; }
+  owner = o; local = lo;
+}
+
+// stage 2: X = clamp(SH2RGB(fdc[id]), 0, 1); flags bit c = gradient passes (0 <= v <= 1).  One thread per 2x2 pixel
+// quad (8-byte id loads, 8-byte X stores); for the batch frames the quad mean is the level-1 pyramid value (avg_pool2d of
+// an even-sized image has no padding), written in the same pass when `xpyr1` is given.
+template <bool W1>
 __global__ void __launch_bounds__(256)
-ssim_bwd_kernel(const float* __restrict__ X, long long x_plane_stride, const float* __restrict__ Y, long long y_frame_stride,
-                long long y_chan_stride, Batch bt, int h, int w, float C1, float C2, const float* __restrict__ coef /*[planes]*/,
-                int use_ssim /* level 4: ssim = l*cs */, const float* __restrict__ d_next, long long dn_plane_stride, int hn, int wn,
-                int ph, int pw, float* __restrict__ dX, long long dx_plane_stride) {
-  extern __shared__ float smem[];
-  float* sx = smem;                                  // [BR][BR]
-  float* sy = sx + BR * BR;                          // [BR][BR]
-  float* vv = sy + BR * BR;                          // [5][BP][BR]   vertical pass
-  float* pm = vv + 5 * BP * BR;                      // [3][BP][BP]   partials dmu1, de11, de12
-  float* tt = vv;                                    // [3][BT][BP]   (reuses vv after partials are built)
-  const int plane = blockIdx.z;
-  const int b = plane / 3, c = plane - 3 * b;
-  const float* xp = X + plane * x_plane_stride;
-  const float* yp = Y + bt.idx[b] * y_frame_stride + c * y_chan_stride;
-  const int oh = h - 10, ow = w - 10;
-  const int qy0 = blockIdx.y * BT, qx0 = blockIdx.x * BT;   // output (image-domain) tile origin
-  const int iy0 = qy0 - 10, ix0 = qx0 - 10;                 // input tile origin == partial-map tile origin
-  const float g_coef = coef[plane];
-  for (int i = threadIdx.x; i < BR * BR; i += blockDim.x) {
-    const int r = i / BR, cc = i - r * BR;
-    const int y = iy0 + r, x = ix0 + cc;
-    const bool in = y >= 0 && y < h && x >= 0 && x < w;
-    sx[i] = in ? xp[(long long)y * w + x] : 0.f;
-    sy[i] = in ? yp[(long long)y * w + x] : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < BP * BR; i += blockDim.x) {
-    const int r = i / BR, cc = i - r * BR;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+uvt_gather_quad_kernel(Shards sh, const int* __restrict__ ids, int H, int W, Batch bt, float* __restrict__ X,
+                       unsigned char* __restrict__ flags, float* __restrict__ xpyr1, long long pyr_plane_stride) {
+  const int h2 = H >> 1, w2 = W >> 1;
+  const long long P = (long long)H * W;
+  const long long quads = (long long)h2 * w2;
+  const long long total = (long long)2 * bt.n * quads;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / quads);
+    const long long qd = i - (long long)f * quads;
+    const int qy = (int)(qd / w2), qx = (int)(qd - (long long)qy * w2);
+    int fr = f < bt.n ? bt.idx[f] : bt.idx[f - bt.n] - 1;
+    if (fr < 0) fr = 0;
+    const long long p0 = (long long)(2 * qy) * W + 2 * qx;
+    const int2 ia = *reinterpret_cast<const int2*>(ids + (long long)fr * P + p0);
+    const int2 ib = *reinterpret_cast<const int2*>(ids + (long long)fr * P + p0 + W);
+    const int id4[4] = {ia.x, ia.y, ib.x, ib.y};
+    float val[4][3];
+    unsigned char fl[4];
 #pragma unroll
-    for (int k = 0; k < 11; ++k) {
-      const float g = c_gauss[k], xv = sx[(r + k) * BR + cc], yv = sy[(r + k) * BR + cc];
-      a0 += g * xv; a1 += g * yv; a2 += g * xv * xv; a3 += g * yv * yv; a4 += g * xv * yv;
-    }
-    vv[(0 * BP + r) * BR + cc] = a0; vv[(1 * BP + r) * BR + cc] = a1; vv[(2 * BP + r) * BR + cc] = a2;
-    vv[(3 * BP + r) * BR + cc] = a3; vv[(4 * BP + r) * BR + cc] = a4;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < BP * BP; i += blockDim.x) {
-    const int r = i / BP, cc = i - r * BP;
-    const int py_ = iy0 + r, px_ = ix0 + cc;     // map position
-    float dmu1 = 0.f, de11 = 0.f, de12 = 0.f;
-    if (py_ >= 0 && py_ < oh && px_ >= 0 && px_ < ow) {
-      SsimMaps m = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < 4; ++k) {
+      int owner, local;
+      shard_of<W1>(sh, id4[k], owner, local);
+      const float* row = sh.fdc[owner] + (long long)local * 3;
+      fl[k] = 0;
 #pragma unroll
-      for (int k = 0; k < 11; ++k) {
-        const float g = c_gauss[k];
-        m.mu1 += g * vv[(0 * BP + r) * BR + cc + k]; m.mu2 += g * vv[(1 * BP + r) * BR + cc + k];
-        m.e11 += g * vv[(2 * BP + r) * BR + cc + k]; m.e22 += g * vv[(3 * BP + r) * BR + cc + k];
-        m.e12 += g * vv[(4 * BP + r) * BR + cc + k];
-      }
-      const float mu1_sq = m.mu1 * m.mu1, mu2_sq = m.mu2 * m.mu2, mu12 = m.mu1 * m.mu2;
-      const float A1 = 2.f * mu12 + C1, B1 = mu1_sq + mu2_sq + C1;
-      const float s11 = m.e11 - mu1_sq, s22 = m.e22 - mu2_sq, s12 = m.e12 - mu12;
-      const float A2 = 2.f * s12 + C2, B2 = s11 + s22 + C2;
-      const float cs = A2 / B2;
-      // d cs / d(e12, e11, mu1)
-      const float dcs_e12 = 2.f / B2;
-      const float dcs_e11 = -A2 / (B2 * B2);
-      const float dcs_mu1 = -2.f * m.mu2 / B2 + 2.f * m.mu1 * A2 / (B2 * B2);
-      if (use_ssim) {
-        const float l = A1 / B1;
-        const float dl_mu1 = (2.f * m.mu2 * B1 - A1 * 2.f * m.mu1) / (B1 * B1);
-        dmu1 = g_coef * (cs * dl_mu1 + l * dcs_mu1);
-        de11 = g_coef * l * dcs_e11;
-        de12 = g_coef * l * dcs_e12;
-      } else {
-        dmu1 = g_coef * dcs_mu1; de11 = g_coef * dcs_e11; de12 = g_coef * dcs_e12;
+      for (int c = 0; c < 3; ++c) {
+        const float v = row[c] * SH_C0 + 0.5f;
+        if (v >= 0.f && v <= 1.f) fl[k] |= (1u << c);
+        val[k][c] = fminf(fmaxf(v, 0.f), 1.f);
       }
     }
-    pm[(0 * BP + r) * BP + cc] = dmu1; pm[(1 * BP + r) * BP + cc] = de11; pm[(2 * BP + r) * BP + cc] = de12;
-  }
-  __syncthreads();
-  // transposed filter, vertical: t[m][qy][px] = sum_k g[k] * pm[m][qy + 10 - k][px]   (map row = q - k)
-  for (int i = threadIdx.x; i < 3 * BT * BP; i += blockDim.x) {
-    const int mI = i / (BT * BP);
-    const int rem = i - mI * BT * BP;
-    const int r = rem / BP, cc = rem - r * BP;
-    float a = 0.f;
 #pragma unroll
-    for (int k = 0; k < 11; ++k) a += c_gauss[k] * pm[(mI * BP + r + 10 - k) * BP + cc];
-    tt[(mI * BT + r) * BP + cc] = a;
-  }
-  __syncthreads();
-  float* dxp = dX + plane * dx_plane_stride;
-  for (int i = threadIdx.x; i < BT * BT; i += blockDim.x) {
-    const int r = i / BT, cc = i - r * BT;
-    const int y = qy0 + r, x = qx0 + cc;
-    if (y < h && x < w) {
-      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll
-      for (int k = 0; k < 11; ++k) {
-        const float g = c_gauss[k];
-        r0 += g * tt[(0 * BT + r) * BP + cc + 10 - k];
-        r1 += g * tt[(1 * BT + r) * BP + cc + 10 - k];
-        r2 += g * tt[(2 * BT + r) * BP + cc + 10 - k];
-      }
-      const float xv = sx[(r + 10) * BR + cc + 10], yv = sy[(r + 10) * BR + cc + 10];
-      float gsum = r0 + 2.f * xv * r1 + yv * r2;
-      if (d_next) {
-        const int oy = (y + ph) >> 1, ox = (x + pw) >> 1;
-        if (oy < hn && ox < wn) gsum += 0.25f * d_next[plane * dn_plane_stride + (long long)oy * wn + ox];
-      }
-      dxp[(long long)y * w + x] = gsum;
+    for (int c = 0; c < 3; ++c) {
+      float* dst = X + ((long long)f * 3 + c) * P + p0;
+      *reinterpret_cast<float2*>(dst) = make_float2(val[0][c], val[1][c]);
+      *reinterpret_cast<float2*>(dst + W) = make_float2(val[2][c], val[3][c]);
+      if (xpyr1 && f < bt.n)
+        xpyr1[((long long)f * 3 + c) * pyr_plane_stride + (long long)qy * w2 + qx] =
+            (val[0][c] + val[1][c] + val[2][c] + val[3][c]) * 0.25f;
     }
+    *reinterpret_cast<uchar2*>(flags + (long long)f * P + p0) = make_uchar2(fl[0], fl[1]);
+    *reinterpret_cast<uchar2*>(flags + (long long)f * P + p0 + W) = make_uchar2(fl[2], fl[3]);
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// producers of X (batch frames then predecessors)
-// ------------------------------------------------------------------------------------------
-// stage 2: X = clamp(SH2RGB(fdc[id]), 0, 1); flags bit c = gradient passes (0 <= v <= 1)
-__global__ void uvt_gather_kernel(const float* __restrict__ fdc, const int* __restrict__ ids, long long P, Batch bt,
+// odd image sizes: one thread per pixel, the pyramid is pooled by avgpool2_kernel afterwards
+template <bool W1>
+__global__ void uvt_gather_kernel(Shards sh, const int* __restrict__ ids, long long P, Batch bt,
                                   float* __restrict__ X, unsigned char* __restrict__ flags) {
   const long long total = (long long)2 * bt.n * P;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -313,11 +405,13 @@ __global__ void uvt_gather_kernel(const float* __restrict__ fdc, const int* __re
     const long long p = i - (long long)f * P;
     int fr = f < bt.n ? bt.idx[f] : bt.idx[f - bt.n] - 1;
     if (fr < 0) fr = 0;
-    const int id = ids[(long long)fr * P + p];
+    int owner, local;
+    shard_of<W1>(sh, ids[(long long)fr * P + p], owner, local);
+    const float* row = sh.fdc[owner] + (long long)local * 3;
     unsigned char fl = 0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float v = fdc[(long long)id * 3 + c] * SH_C0 + 0.5f;
+      const float v = row[c] * SH_C0 + 0.5f;
       if (v >= 0.f && v <= 1.f) fl |= (1u << c);
       X[((long long)f * 3 + c) * P + p] = fminf(fmaxf(v, 0.f), 1.f);
     }
@@ -371,22 +465,201 @@ struct L0Params {
   const unsigned char* flags;     // [2n,P]
   const float* flows;             // [N,2,P]
   const float* mask;              // [N,1,P]
-  const float* d1;                // level-1 gradient [n*3 planes]
-  long long d1_stride; int h1, w1, ph0, pw0;
+  const float* own;               // per-level MS-SSIM gradients [n*3 planes][pyramid] (ssim_bwd_all_kernel)
+  long long own_stride;
+  Pyr py;
   float k_flow;                   // lambda_flow / (n_valid*3*P)
   float k_tvh, k_tvw;             // lambda_tv*2/(count_h*n), lambda_tv*2/(count_w*n)
   float k_l1;                     // stage 1: (1-lambda_flow)*(1-lambda_dssim)/(n*3*P); 0 in stage 2
   const float* edited;            // [N,3,P] (stage 1 L1 target and affine input)
-  float* G_pre;                   // [n,P,4] atomically accumulated predecessor gradient (lane 3 unused)
+  float* G_pre;                   // stage 1: [n,P,4] atomically accumulated predecessor gradient (lane 3 unused)
   float* scal;
   // sinks
-  const int* ids; float* grad_fdc;        // stage 2: [U,4] (lane 3 unused)
+  const int* ids;                         // stage 2: unq_inv [N*P]
   float* grad_expo;                       // stage 1: [N,12]
 };
 
-template <int MODE /*0 = UVT, 1 = exposure*/>
+// d(loss)/dX at level 0 coming from MS-SSIM: the avg-pool backward chain of levels 1..4
+//   dX_0 = 1/4 up(own_1 + 1/4 up(own_2 + 1/4 up(own_3 + 1/4 up(own_4))))     (up = nearest, with the pooling padding)
+__device__ __forceinline__ float msssim_grad(const float* __restrict__ own_plane, const Pyr& py, int y, int x) {
+  float g = 0.f, wgt = 0.25f;
+#pragma unroll
+  for (int l = 1; l <= 4; ++l) {
+    y = (y + py.ph[l - 1]) >> 1;
+    x = (x + py.pw[l - 1]) >> 1;
+    if (y >= py.h[l] || x >= py.w[l]) break;
+    g += wgt * own_plane[py.off[l] + (long long)y * py.w[l] + x];
+    wgt *= 0.25f;
+  }
+  return g;
+}
+
+struct Bicubic {
+  float cx[4], cy[4];
+  int x0, y0;
+};
+__device__ __forceinline__ void bicubic_setup(const L0Params& q, int fr, long long p, int x, int y, Bicubic& bc) {
+  const float fx = q.flows[((long long)fr * 2 + 0) * q.P + p] + (float)x;
+  const float fy = q.flows[((long long)fr * 2 + 1) * q.P + p] + (float)y;
+  const float gx = (fx / (float)(q.W - 1) - 0.5f) * 2.f;
+  const float gy = (fy / (float)(q.H - 1) - 0.5f) * 2.f;
+  const float ix = ((gx + 1.f) / 2.f) * (float)(q.W - 1);
+  const float iy = ((gy + 1.f) / 2.f) * (float)(q.H - 1);
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  cubic_coeffs(ix - fx0, bc.cx);
+  cubic_coeffs(iy - fy0, bc.cy);
+  bc.x0 = (int)fx0 - 1; bc.y0 = (int)fy0 - 1;
+}
+__device__ __forceinline__ void bicubic_sample(const L0Params& q, const float* __restrict__ Xp, const Bicubic& bc, float (&wv)[3]) {
+  wv[0] = wv[1] = wv[2] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int yy = bc.y0 + j;
+    if (yy < 0 || yy >= q.H) continue;
+    float row[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int xx = bc.x0 + i;
+      if (xx < 0 || xx >= q.W) continue;
+      const long long o = (long long)yy * q.W + xx;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) row[c] += Xp[c * q.P + o] * bc.cx[i];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) wv[c] += row[c] * bc.cy[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage 2, fused level-0 kernel: bicubic flow warp forward + backward, masked L1, TV, MS-SSIM gradient chain, and the
+// gradient sinks — every pixel's dLoss/dX goes straight into the UVT gradient row of its id (local or peer shard).
+// The bicubic backward would be 16 reductions per pixel; instead the four taps of a row are summed across the warp
+// first: neighbouring pixels of a smooth flow hit neighbouring columns, so tap i of lane l and tap i-1 of lane l+1 land
+// on the same predecessor pixel.  The partial sums travel one lane to the right per stage (3 shuffles per channel and
+// row) and a lane only issues a reduction where its chain ends: ~1 reduction per pixel and row instead of 4.
+// ------------------------------------------------------------------------------------------
+template <bool W1>
 __global__ void __launch_bounds__(256)
-level0_kernel(L0Params q) {
+level0_uvt_kernel(L0Params q, Shards sh) {
+  __shared__ float red[3][8];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int fr = q.bt.idx[b];
+  const bool valid = fr > 0;
+  const float* Xi = q.X + (long long)b * 3 * q.P;
+  const float* Xp = q.X + (long long)(q.bt.n + b) * 3 * q.P;
+  const unsigned char* fl_pre = q.flags + (long long)(q.bt.n + b) * q.P;
+  const int* ids_pre = q.ids + (long long)(fr > 0 ? fr - 1 : 0) * q.P;
+  float acc_flow = 0.f, acc_tvh = 0.f, acc_tvw = 0.f;
+
+  auto sink = [&](int id, unsigned fl, float g0, float g1, float g2) {
+    if (!(fl & 7)) return;
+    int owner, local;
+    shard_of<W1>(sh, id, owner, local);
+    red_add_v4(sh.grad[owner] + (long long)local * 4, (fl & 1) ? g0 * SH_C0 : 0.f, (fl & 2) ? g1 * SH_C0 : 0.f,
+               (fl & 4) ? g2 * SH_C0 : 0.f);
+  };
+
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long pw = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); pw < q.P; pw += stride) {   // warp-uniform trip count
+    const long long p = pw + lane;
+    const bool act = p < q.P;
+    const int x = act ? (int)(p % q.W) : 0, y = act ? (int)(p / q.W) : 0;
+    float xi[3] = {0.f, 0.f, 0.f}, g[3] = {0.f, 0.f, 0.f};
+    if (act) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) xi[c] = Xi[c * q.P + p];
+    }
+    // ---- flow term: warp the predecessor with the backward flow ----
+    if (valid) {
+      Bicubic bc;
+      bc.x0 = bc.y0 = -(1 << 20);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bc.cx[i] = bc.cy[i] = 0.f;
+      float s[3] = {0.f, 0.f, 0.f};
+      if (act) {
+        bicubic_setup(q, fr, p, x, y, bc);
+        float wv[3];
+        bicubic_sample(q, Xp, bc, wv);
+        const float m = q.mask[(long long)fr * q.P + p];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float d = wv[c] * m - xi[c] * m;
+          acc_flow += fabsf(d);
+          const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+          s[c] = sg * m * q.k_flow;
+          g[c] -= s[c];
+        }
+      }
+      // links of the systolic row sums: lane l continues the chain of lane l-1 iff their footprints are one column apart
+      const int x0l = __shfl_up_sync(FULL, bc.x0, 1), y0l = __shfl_up_sync(FULL, bc.y0, 1);
+      const bool link = lane > 0 && bc.x0 == x0l + 1 && bc.y0 == y0l;
+      const int link_next = __shfl_down_sync(FULL, (int)link, 1);     // every lane shuffles (no short-circuit around a .sync)
+      const bool link_r = lane < 31 && link_next;
+      auto flush = [&](float a0, float a1, float a2, int xx, int yy) {
+        if (xx < 0 || xx >= q.W || yy < 0 || yy >= q.H) return;
+        if (a0 == 0.f && a1 == 0.f && a2 == 0.f) return;
+        const long long o = (long long)yy * q.W + xx;
+        sink(ids_pre[o], fl_pre[o], a0, a1, a2);
+      };
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int yy = bc.y0 + j;
+        const float wy = bc.cy[j];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int st = 0; st < 4; ++st) {
+          const float wgt = bc.cx[3 - st] * wy;
+          if (st > 0) {
+            const float r0 = __shfl_up_sync(FULL, a0, 1), r1 = __shfl_up_sync(FULL, a1, 1), r2 = __shfl_up_sync(FULL, a2, 1);
+            a0 = link ? r0 : 0.f; a1 = link ? r1 : 0.f; a2 = link ? r2 : 0.f;
+          }
+          a0 += s[0] * wgt; a1 += s[1] * wgt; a2 += s[2] * wgt;
+          if (st == 3 || !link_r) flush(a0, a1, a2, bc.x0 + 3 - st, yy);
+        }
+      }
+    }
+    if (!act) continue;
+    // ---- total variation ----
+    if (q.k_tvh != 0.f) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* pl = Xi + c * q.P;
+        const float v = xi[c];
+        float gg = 0.f;
+        if (y + 1 < q.H) { const float d = pl[p + q.W] - v; acc_tvh += d * d; gg -= q.k_tvh * 2.f * d; }
+        if (y > 0) gg += q.k_tvh * 2.f * (v - pl[p - q.W]);
+        if (x + 1 < q.W) { const float d = pl[p + 1] - v; acc_tvw += d * d; gg -= q.k_tvw * 2.f * d; }
+        if (x > 0) gg += q.k_tvw * 2.f * (v - pl[p - 1]);
+        g[c] += gg;
+      }
+    }
+    // ---- MS-SSIM gradient chain ----
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] += msssim_grad(q.own + (long long)(b * 3 + c) * q.own_stride, q.py, y, x);
+    // ---- sink ----
+    sink(q.ids[(long long)fr * q.P + p], q.flags[(long long)b * q.P + p], g[0], g[1], g[2]);
+  }
+  acc_flow = warp_sum(acc_flow); acc_tvh = warp_sum(acc_tvh); acc_tvw = warp_sum(acc_tvw);
+  if (lane == 0) {
+    const int wq = threadIdx.x >> 5;
+    red[0][wq] = acc_flow; red[1][wq] = acc_tvh; red[2][wq] = acc_tvw;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, bb = 0.f, cc = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; bb += red[1][i]; cc += red[2][i]; }
+    atomicAdd(&q.scal[SC_FLOW_ABS], a); atomicAdd(&q.scal[SC_TV_H], bb); atomicAdd(&q.scal[SC_TV_W], cc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage 1, fused level-0 kernel over the batch frames (the exposure gradient is 12 numbers per frame: the bicubic
+// backward is accumulated per predecessor pixel in G_pre and folded by pre_sink_kernel)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+level0_expo_kernel(L0Params q) {
   __shared__ float red[4][8];
   __shared__ float eg[12];
   const int b = blockIdx.y;
@@ -394,46 +667,21 @@ level0_kernel(L0Params q) {
   const bool valid = fr > 0;
   const float* Xi = q.X + (long long)b * 3 * q.P;
   const float* Xp = q.X + (long long)(q.bt.n + b) * 3 * q.P;
-  float acc_flow = 0.f, acc_tvh = 0.f, acc_tvw = 0.f, acc_l1 = 0.f;
+  float acc_flow = 0.f, acc_l1 = 0.f;
   float ge[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) ge[k] = 0.f;
-  if (MODE == 1 && threadIdx.x < 12) eg[threadIdx.x] = 0.f;
+  if (threadIdx.x < 12) eg[threadIdx.x] = 0.f;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < q.P; p += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(p % q.W), y = (int)(p / q.W);
     float xi[3], g[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) { xi[c] = Xi[c * q.P + p]; g[c] = 0.f; }
-    // ---- flow term: warp the predecessor with the backward flow ----
     if (valid) {
-      const float fx = q.flows[((long long)fr * 2 + 0) * q.P + p] + (float)x;
-      const float fy = q.flows[((long long)fr * 2 + 1) * q.P + p] + (float)y;
-      const float gx = (fx / (float)(q.W - 1) - 0.5f) * 2.f;
-      const float gy = (fy / (float)(q.H - 1) - 0.5f) * 2.f;
-      const float ix = ((gx + 1.f) / 2.f) * (float)(q.W - 1);
-      const float iy = ((gy + 1.f) / 2.f) * (float)(q.H - 1);
-      const float fx0 = floorf(ix), fy0 = floorf(iy);
-      float cx[4], cy[4];
-      cubic_coeffs(ix - fx0, cx);
-      cubic_coeffs(iy - fy0, cy);
-      const int x0 = (int)fx0 - 1, y0 = (int)fy0 - 1;
-      float wv[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int yy = y0 + j;
-        if (yy < 0 || yy >= q.H) continue;
-        float row[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int xx = x0 + i;
-          if (xx < 0 || xx >= q.W) continue;
-          const long long o = (long long)yy * q.W + xx;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) row[c] += Xp[c * q.P + o] * cx[i];
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) wv[c] += row[c] * cy[j];
-      }
+      Bicubic bc;
+      bicubic_setup(q, fr, p, x, y, bc);
+      float wv[3];
+      bicubic_sample(q, Xp, bc, wv);
       const float m = q.mask[(long long)fr * q.P + p];
       float s[3];
 #pragma unroll
@@ -448,92 +696,54 @@ level0_kernel(L0Params q) {
       if (s[0] != 0.f || s[1] != 0.f || s[2] != 0.f) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int yy = y0 + j;
+          const int yy = bc.y0 + j;
           if (yy < 0 || yy >= q.H) continue;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int xx = x0 + i;
+            const int xx = bc.x0 + i;
             if (xx < 0 || xx >= q.W) continue;
-            const float wgt = cx[i] * cy[j];
-            const long long o = (long long)yy * q.W + xx;
-            red_add_v4(Gp + o * 4, s[0] * wgt, s[1] * wgt, s[2] * wgt);
+            const float wgt = bc.cx[i] * bc.cy[j];
+            red_add_v4(Gp + ((long long)yy * q.W + xx) * 4, s[0] * wgt, s[1] * wgt, s[2] * wgt);
           }
         }
       }
     }
-    // ---- total variation (stage 2) ----
-    if (q.k_tvh != 0.f) {
+    // ---- L1 to the target ----
+    float in[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float* pl = Xi + c * q.P;
-        const float v = xi[c];
-        float gg = 0.f;
-        if (y + 1 < q.H) { const float d = pl[p + q.W] - v; acc_tvh += d * d; gg -= q.k_tvh * 2.f * d; }
-        if (y > 0) gg += q.k_tvh * 2.f * (v - pl[p - q.W]);
-        if (x + 1 < q.W) { const float d = pl[p + 1] - v; acc_tvw += d * d; gg -= q.k_tvw * 2.f * d; }
-        if (x > 0) gg += q.k_tvw * 2.f * (v - pl[p - 1]);
-        g[c] += gg;
-      }
+    for (int c = 0; c < 3; ++c) {
+      in[c] = q.edited[((long long)fr * 3 + c) * q.P + p];
+      const float d = xi[c] - in[c];
+      acc_l1 += fabsf(d);
+      g[c] += q.k_l1 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
     }
-    // ---- L1 to the target (stage 1) ----
-    float in[3] = {0.f, 0.f, 0.f};
-    if (MODE == 1) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        in[c] = q.edited[((long long)fr * 3 + c) * q.P + p];
-        const float d = xi[c] - in[c];
-        acc_l1 += fabsf(d);
-        g[c] += q.k_l1 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
-      }
-    }
-    // ---- MS-SSIM gradient from level 1 (avg-pool backward) ----
-    {
-      const int oy = (y + q.ph0) >> 1, ox = (x + q.pw0) >> 1;
-      if (oy < q.h1 && ox < q.w1) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) g[c] += 0.25f * q.d1[(long long)(b * 3 + c) * q.d1_stride + (long long)oy * q.w1 + ox];
-      }
-    }
-    // ---- sink ----
+    for (int c = 0; c < 3; ++c) g[c] += msssim_grad(q.own + (long long)(b * 3 + c) * q.own_stride, q.py, y, x);
     const unsigned char fl = q.flags[(long long)b * q.P + p];
-    if (MODE == 0) {
-      const int id = q.ids[(long long)fr * q.P + p];
-      if (fl & 7)
-        red_add_v4(q.grad_fdc + (long long)id * 4, (fl & 1) ? g[0] * SH_C0 : 0.f, (fl & 2) ? g[1] * SH_C0 : 0.f,
-                   (fl & 4) ? g[2] * SH_C0 : 0.f);
-    } else {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float gj = ((fl >> j) & 1) ? g[j] : 0.f;
-        ge[0 * 4 + j] += gj * in[0]; ge[1 * 4 + j] += gj * in[1]; ge[2 * 4 + j] += gj * in[2];
-        ge[j * 4 + 3] += gj;
-      }
+    for (int j = 0; j < 3; ++j) {
+      const float gj = ((fl >> j) & 1) ? g[j] : 0.f;
+      ge[0 * 4 + j] += gj * in[0]; ge[1 * 4 + j] += gj * in[1]; ge[2 * 4 + j] += gj * in[2];
+      ge[j * 4 + 3] += gj;
     }
   }
-  // block reductions
-  acc_flow = warp_sum(acc_flow); acc_tvh = warp_sum(acc_tvh); acc_tvw = warp_sum(acc_tvw); acc_l1 = warp_sum(acc_l1);
-  if ((threadIdx.x & 31) == 0) {
-    const int wq = threadIdx.x >> 5;
-    red[0][wq] = acc_flow; red[1][wq] = acc_tvh; red[2][wq] = acc_tvw; red[3][wq] = acc_l1;
-  }
-  if (MODE == 1) {
+  acc_flow = warp_sum(acc_flow); acc_l1 = warp_sum(acc_l1);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = acc_flow; red[3][threadIdx.x >> 5] = acc_l1; }
 #pragma unroll
-    for (int k = 0; k < 12; ++k) {
-      const float r = warp_sum(ge[k]);
-      if ((threadIdx.x & 31) == 0 && r != 0.f) atomicAdd(&eg[k], r);
-    }
+  for (int k = 0; k < 12; ++k) {
+    const float r = warp_sum(ge[k]);
+    if ((threadIdx.x & 31) == 0 && r != 0.f) atomicAdd(&eg[k], r);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float a = 0.f, bb = 0.f, cc = 0.f, dd = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; bb += red[1][i]; cc += red[2][i]; dd += red[3][i]; }
-    atomicAdd(&q.scal[SC_FLOW_ABS], a); atomicAdd(&q.scal[SC_TV_H], bb); atomicAdd(&q.scal[SC_TV_W], cc); atomicAdd(&q.scal[SC_L1], dd);
+    float a = 0.f, dd = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; dd += red[3][i]; }
+    atomicAdd(&q.scal[SC_FLOW_ABS], a); atomicAdd(&q.scal[SC_L1], dd);
   }
-  if (MODE == 1 && threadIdx.x < 12) atomicAdd(&q.grad_expo[(long long)fr * 12 + threadIdx.x], eg[threadIdx.x]);
+  if (threadIdx.x < 12) atomicAdd(&q.grad_expo[(long long)fr * 12 + threadIdx.x], eg[threadIdx.x]);
 }
 
-// predecessor half: G_pre -> clamp mask -> sink; clears G_pre for the next iteration
-template <int MODE>
+// stage 1, predecessor half: G_pre -> clamp mask -> exposure gradient of frame idx-1; clears G_pre for the next iteration
 __global__ void __launch_bounds__(256)
 pre_sink_kernel(L0Params q) {
   __shared__ float eg[12];
@@ -543,7 +753,7 @@ pre_sink_kernel(L0Params q) {
   float ge[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) ge[k] = 0.f;
-  if (MODE == 1 && threadIdx.x < 12) eg[threadIdx.x] = 0.f;
+  if (threadIdx.x < 12) eg[threadIdx.x] = 0.f;
   float4* Gp = reinterpret_cast<float4*>(q.G_pre + (long long)b * 4 * q.P);
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < q.P; p += (long long)gridDim.x * blockDim.x) {
     const float4 gv = Gp[p];
@@ -551,32 +761,23 @@ pre_sink_kernel(L0Params q) {
     Gp[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float g[3] = {gv.x, gv.y, gv.z};
     const unsigned char fl = q.flags[(long long)(q.bt.n + b) * q.P + p];
-    if (MODE == 0) {
-      const int id = q.ids[(long long)fr * q.P + p];
-      if (fl & 7)
-        red_add_v4(q.grad_fdc + (long long)id * 4, (fl & 1) ? g[0] * SH_C0 : 0.f, (fl & 2) ? g[1] * SH_C0 : 0.f,
-                   (fl & 4) ? g[2] * SH_C0 : 0.f);
-    } else {
-      float in[3];
+    float in[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) in[c] = q.edited[((long long)fr * 3 + c) * q.P + p];
+    for (int c = 0; c < 3; ++c) in[c] = q.edited[((long long)fr * 3 + c) * q.P + p];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float gj = ((fl >> j) & 1) ? g[j] : 0.f;
-        ge[0 * 4 + j] += gj * in[0]; ge[1 * 4 + j] += gj * in[1]; ge[2 * 4 + j] += gj * in[2];
-        ge[j * 4 + 3] += gj;
-      }
+    for (int j = 0; j < 3; ++j) {
+      const float gj = ((fl >> j) & 1) ? g[j] : 0.f;
+      ge[0 * 4 + j] += gj * in[0]; ge[1 * 4 + j] += gj * in[1]; ge[2 * 4 + j] += gj * in[2];
+      ge[j * 4 + 3] += gj;
     }
   }
-  if (MODE == 1) {
 #pragma unroll
-    for (int k = 0; k < 12; ++k) {
-      const float r = warp_sum(ge[k]);
-      if ((threadIdx.x & 31) == 0 && r != 0.f) atomicAdd(&eg[k], r);
-    }
-    __syncthreads();
-    if (threadIdx.x < 12) atomicAdd(&q.grad_expo[(long long)fr * 12 + threadIdx.x], eg[threadIdx.x]);
+  for (int k = 0; k < 12; ++k) {
+    const float r = warp_sum(ge[k]);
+    if ((threadIdx.x & 31) == 0 && r != 0.f) atomicAdd(&eg[k], r);
   }
+  __syncthreads();
+  if (threadIdx.x < 12) atomicAdd(&q.grad_expo[(long long)fr * 12 + threadIdx.x], eg[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -742,35 +943,41 @@ static int ensure_gauss() {
 
 // workspace carving ---------------------------------------------------------------------
 struct Ws {
-  float* X; unsigned char* flags; float* G_pre; float* xpyr; float* dpyr; float* sums; float* coef; float* scal;
+  float* X; unsigned char* flags; float* G_pre; float* xpyr; float* pm; float* own; float* sums; float* coef; float* scal;
 };
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
-static size_t ws_bytes(int H, int W, int nb) {
-  Pyr py; make_pyr(H, W, &py);
-  const size_t P = (size_t)H * W;
-  size_t b = 0;
-  b += align_up(sizeof(float) * 2 * nb * 3 * P);          // X
-  b += align_up((size_t)2 * nb * P);                      // flags
-  b += align_up(sizeof(float) * nb * 4 * P);              // G_pre [nb,P,4]
-  b += align_up(sizeof(float) * nb * 3 * py.total);       // X pyramid levels 1..4
-  b += align_up(sizeof(float) * nb * 3 * py.total);       // dX pyramid
-  b += align_up(sizeof(float) * 4 * nb * 3 * 2);          // sums
-  b += align_up(sizeof(float) * 4 * nb * 3);              // coef
-  b += align_up(sizeof(float) * SC_COUNT);                // scalars
-  return b;
-}
-static void carve(void* base, int H, int W, int nb, Ws* w) {
+static size_t ws_layout(void* base, int H, int W, int nb, Ws* w) {
   Pyr py; make_pyr(H, W, &py);
   const size_t P = (size_t)H * W;
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
-  w->X = (float*)p; p += align_up(sizeof(float) * 2 * nb * 3 * P);
-  w->flags = p; p += align_up((size_t)2 * nb * P);
-  w->G_pre = (float*)p; p += align_up(sizeof(float) * nb * 4 * P);
-  w->xpyr = (float*)p; p += align_up(sizeof(float) * nb * 3 * py.total);
-  w->dpyr = (float*)p; p += align_up(sizeof(float) * nb * 3 * py.total);
-  w->sums = (float*)p; p += align_up(sizeof(float) * 4 * nb * 3 * 2);
-  w->coef = (float*)p; p += align_up(sizeof(float) * 4 * nb * 3);
-  w->scal = (float*)p;
+  auto take = [&](size_t bytes) { uint8_t* r = p; p += align_up(bytes); return r; };
+  Ws t;
+  t.X = (float*)take(sizeof(float) * 2 * nb * 3 * P);
+  t.flags = take((size_t)2 * nb * P);
+  t.G_pre = (float*)take(sizeof(float) * nb * 4 * P);             // stage 1 only: [nb,P,4], zero between iterations
+  t.xpyr = (float*)take(sizeof(float) * nb * 3 * py.total);       // X pyramid levels 1..4
+  t.pm = (float*)take(sizeof(float) * nb * 3 * 3 * py.total);     // d(map)/d(mu1, e11, e12) per level
+  t.own = (float*)take(sizeof(float) * nb * 3 * py.total);        // per-level MS-SSIM gradient
+  t.sums = (float*)take(sizeof(float) * (4 * nb * 3 * 2 + SC_COUNT));   // level sums, then the scalars (one memset)
+  t.scal = t.sums + 4 * nb * 3 * 2;
+  t.coef = (float*)take(sizeof(float) * 4 * nb * 3);
+  if (w) *w = t;
+  return (size_t)(p - reinterpret_cast<uint8_t*>(base));
+}
+static size_t ws_bytes(int H, int W, int nb) { return ws_layout(nullptr, H, W, nb, nullptr); }
+
+static void make_plan(const Pyr& py, int planes, bool map_domain, int only_level, LevelPlan* lp) {
+  int first = 0;
+  for (int l = 1; l <= 4; ++l) {
+    lp->h[l] = py.h[l]; lp->w[l] = py.w[l]; lp->off[l] = py.off[l];
+    const int dh = map_domain ? py.h[l] - 10 : py.h[l], dw = map_domain ? py.w[l] - 10 : py.w[l];
+    lp->tiles_x[l] = (dw + ST - 1) / ST; lp->tiles_y[l] = (dh + ST - 1) / ST;
+    lp->first[l] = first;
+    if (only_level == 0 || only_level == l) first += lp->tiles_x[l] * lp->tiles_y[l] * planes;
+  }
+  lp->h[0] = lp->w[0] = 0; lp->off[0] = 0; lp->tiles_x[0] = lp->tiles_y[0] = 0; lp->first[0] = 0;
+  lp->first[5] = first;
+  lp->planes = planes;
 }
 
 }  // namespace tcl
@@ -799,13 +1006,22 @@ extern "C" int tcl_postopt_build_pyramid(const float* edited, int N, int H, int 
   return TCL_OK;
 }
 
+static int check_shards(const tcl_uvt_shards* s, const char* who) {
+  TCL_CHECK_ARG(s && s->world >= 1 && s->world <= TCL_MAX_RANKS && s->rank >= 0 && s->rank < s->world && s->rows_per_rank > 0,
+                "%s: bad shard table (world %d, rank %d)", who, s ? s->world : -1, s ? s->rank : -1);
+  TCL_CHECK_ARG(s->world == 1 || (s->rows_per_rank >= 256 && s->rows_per_rank % 4 == 0),
+                "%s: rows_per_rank must be a multiple of 4 and >= 256 when world > 1", who);
+  for (int r = 0; r < s->world; ++r) TCL_CHECK_ARG(s->fdc[r] && s->grad[r], "%s: null shard pointer (rank %d)", who, r);
+  return TCL_OK;
+}
+
+// One optimiser iteration.  stage 2: `shards` names where the UVT rows and their gradient live (one entry on a single
+// GPU); stage 1: expo/egrad.  `adam`: 0 = gradient only, 1 = gradient + Adam over the LOCAL shard / the exposure table.
 static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_host, int nb,
-                         // stage 2
-                         const int* ids, long long U, float* fdc, float* grad, float* m, float* v,
-                         // stage 1
+                         const int* ids, const tcl_uvt_shards* shards, float* m, float* v,
                          float* expo, float* egrad, float* em, float* ev,
                          float lr, float beta1, float beta2, float eps, int step, float* loss_out, cudaStream_t stream,
-                         bool do_adam = true) {
+                         bool do_adam) {
   TCL_CHECK_ARG(c && idx_host && nb > 0 && nb <= MAXB, "postopt: batch size %d (max %d)", nb, MAXB);
   TCL_CHECK_ARG(c->edited && c->past_flows && c->mask_bwd && c->ypyr && c->workspace, "postopt: null context pointer");
   TCL_CHECK_ARG(c->max_batch >= nb && c->max_batch <= MAXB, "postopt: batch %d exceeds ctx.max_batch %d", nb, c->max_batch);
@@ -820,7 +1036,7 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
   const long long P = (long long)H * W;
   Pyr py; make_pyr(H, W, &py);
   TCL_CHECK_ARG(py.h[4] >= 11 && py.w[4] >= 11, "postopt: image too small for 5-level MS-SSIM");
-  Ws w; carve(c->workspace, H, W, c->max_batch, &w);   // fixed layout: G_pre must stay zero between iterations
+  Ws w; ws_layout(c->workspace, H, W, c->max_batch, &w);   // fixed layout: G_pre must stay zero between iterations
   Batch bt; bt.n = nb;
   int n_valid = 0;
   for (int i = 0; i < nb; ++i) {
@@ -830,14 +1046,33 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
   }
   for (int i = nb; i < MAXB; ++i) bt.idx[i] = 0;
   const int planes = nb * 3;
-  cudaMemsetAsync(w.sums, 0, sizeof(float) * 4 * planes * 2, stream);
-  cudaMemsetAsync(w.scal, 0, sizeof(float) * SC_COUNT, stream);
-  // 1. produce X
-  if (stage == 2) uvt_gather_kernel<<<gridp(2 * nb * P, 256, 148 * 16), 256, 0, stream>>>(fdc, ids, P, bt, w.X, w.flags);
-  else exposure_apply_kernel<<<gridp(2 * nb * P, 256, 148 * 16), 256, 0, stream>>>(c->edited, expo, P, bt, w.X, w.flags);
+  Shards sh;
+  memset(&sh, 0, sizeof(sh));
+  bool w1 = true;
+  if (stage == 2) {
+    sh.world = shards->world; sh.rows_per_rank = (int)shards->rows_per_rank; sh.inv_rows = 1.f / (float)shards->rows_per_rank;
+    for (int r = 0; r < shards->world; ++r) { sh.fdc[r] = shards->fdc[r]; sh.grad[r] = shards->grad[r]; }
+    w1 = shards->world == 1;
+  }
+  cudaMemsetAsync(w.sums, 0, sizeof(float) * (4 * c->max_batch * 3 * 2 + SC_COUNT), stream);
+  // 1. produce X (and, for even sizes in stage 2, level 1 of the pyramid in the same pass)
+  int first_pool = 0;
+  if (stage == 2) {
+    if (H % 2 == 0 && W % 2 == 0) {
+      const long long quads = (long long)2 * nb * (P / 4);
+      if (w1) uvt_gather_quad_kernel<true><<<gridp(quads, 256, 148 * 16), 256, 0, stream>>>(sh, ids, H, W, bt, w.X, w.flags, w.xpyr + py.off[1], py.total);
+      else uvt_gather_quad_kernel<false><<<gridp(quads, 256, 148 * 16), 256, 0, stream>>>(sh, ids, H, W, bt, w.X, w.flags, w.xpyr + py.off[1], py.total);
+      first_pool = 1;
+    } else {
+      if (w1) uvt_gather_kernel<true><<<gridp(2 * nb * P, 256, 148 * 16), 256, 0, stream>>>(sh, ids, P, bt, w.X, w.flags);
+      else uvt_gather_kernel<false><<<gridp(2 * nb * P, 256, 148 * 16), 256, 0, stream>>>(sh, ids, P, bt, w.X, w.flags);
+    }
+  } else {
+    exposure_apply_kernel<<<gridp(2 * nb * P, 256, 148 * 16), 256, 0, stream>>>(c->edited, expo, P, bt, w.X, w.flags);
+  }
   TCL_CHECK_LAUNCH("postopt(produce)");
   // 2. pyramid of the batch frames
-  for (int l = 0; l < 4; ++l) {
+  for (int l = first_pool; l < 4; ++l) {
     const float* in = l == 0 ? w.X : w.xpyr + py.off[l];
     const long long in_stride = l == 0 ? P : py.total;
     const long long total = (long long)planes * py.h[l + 1] * py.w[l + 1];
@@ -845,53 +1080,45 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
                                                            w.xpyr + py.off[l + 1], py.total, py.h[l + 1], py.w[l + 1], planes);
     TCL_CHECK_LAUNCH("postopt(pyramid)");
   }
-  // 3. SSIM forward per level
+  // 3. relaxed-SSIM forward, all levels in one launch
   const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;   // data_range = 1
-  for (int l = 1; l <= 4; ++l) {
-    dim3 grid((py.w[l] - 10 + ST - 1) / ST, (py.h[l] - 10 + ST - 1) / ST, planes);
-    ssim_fwd_kernel<<<grid, 256, 0, stream>>>(w.xpyr + py.off[l], py.total, c->ypyr + py.off[l], 3 * py.total, py.total, bt,
-                                              py.h[l], py.w[l], C1, C2, w.sums + (size_t)(l - 1) * planes * 2);
-    TCL_CHECK_LAUNCH("postopt(ssim_fwd)");
-  }
+  LevelPlan lpf, lpb;
+  make_plan(py, planes, true, 0, &lpf);
+  make_plan(py, planes, false, 0, &lpb);
+  ssim_fwd_all_kernel<<<lpf.first[5], 256, 0, stream>>>(w.xpyr, py.total, c->ypyr, 3 * py.total, py.total, bt, lpf, C1, C2, w.sums,
+                                                        w.pm, py.total);
+  TCL_CHECK_LAUNCH("postopt(ssim_fwd)");
   // 4. loss head
   const int planes_g = nb_g * 3;
   const float k_ms = -(1.f - c->lambda_flow) * c->lambda_dssim / (float)planes_g;
   msssim_head_kernel<<<1, 64, 0, stream>>>(w.sums, planes, py, k_ms, w.coef, w.scal);
   TCL_CHECK_LAUNCH("postopt(head)");
-  // 5. SSIM backward 4 -> 1
-  static bool bwd_conf = false;
-  const size_t bwd_smem = sizeof(float) * (2 * BR * BR + 5 * BP * BR + 3 * BP * BP);
-  if (!bwd_conf) {
-    cudaError_t e = cudaFuncSetAttribute(ssim_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem);
-    if (e != cudaSuccess) { set_last_error("postopt: smem attr: %s", cudaGetErrorString(e)); return TCL_ERR_CUDA; }
-    bwd_conf = true;
-  }
-  for (int l = 4; l >= 1; --l) {
-    dim3 grid((py.w[l] + BT - 1) / BT, (py.h[l] + BT - 1) / BT, planes);
-    const float* dn = l < 4 ? w.dpyr + py.off[l + 1] : nullptr;
-    ssim_bwd_kernel<<<grid, 256, bwd_smem, stream>>>(w.xpyr + py.off[l], py.total, c->ypyr + py.off[l], 3 * py.total, py.total, bt,
-                                                     py.h[l], py.w[l], C1, C2, w.coef + (size_t)(l - 1) * planes, l == 4 ? 1 : 0,
-                                                     dn, py.total, l < 4 ? py.h[l + 1] : 0, l < 4 ? py.w[l + 1] : 0, py.ph[l], py.pw[l],
-                                                     w.dpyr + py.off[l], py.total);
-    TCL_CHECK_LAUNCH("postopt(ssim_bwd)");
-  }
-  // 6. fused level-0 kernel + predecessor sink
+  // 5. relaxed-SSIM backward, all levels in one launch
+  ssim_bwd_all_kernel<<<lpb.first[5], 256, 0, stream>>>(w.xpyr, py.total, c->ypyr, 3 * py.total, py.total, bt, lpb, w.coef, w.pm,
+                                                        py.total, w.own, py.total);
+  TCL_CHECK_LAUNCH("postopt(ssim_bwd)");
+  // 6. fused level-0 kernel (+ stage 1: predecessor sink)
   L0Params q;
   memset(&q, 0, sizeof(q));
   q.H = H; q.W = W; q.P = P; q.bt = bt; q.X = w.X; q.flags = w.flags; q.flows = c->past_flows; q.mask = c->mask_bwd;
-  q.d1 = w.dpyr + py.off[1]; q.d1_stride = py.total; q.h1 = py.h[1]; q.w1 = py.w[1]; q.ph0 = py.ph[0]; q.pw0 = py.pw[0];
+  q.own = w.own; q.own_stride = py.total; q.py = py;
   const int n_valid_g = c->norm_batch > 0 ? c->norm_valid : n_valid;
   const float flow_cnt = (float)n_valid_g * 3.f * (float)P;
   q.k_flow = n_valid_g > 0 ? c->lambda_flow / flow_cnt : 0.f;
   const float count_h = 3.f * (float)(H - 1) * (float)W, count_w = 3.f * (float)H * (float)(W - 1);
   if (stage == 2) { q.k_tvh = c->lambda_tv * 2.f / (count_h * nb_g); q.k_tvw = c->lambda_tv * 2.f / (count_w * nb_g); }
   q.k_l1 = stage == 1 ? (1.f - c->lambda_flow) * (1.f - c->lambda_dssim) / ((float)planes_g * (float)P) : 0.f;
-  q.edited = c->edited; q.G_pre = w.G_pre; q.scal = w.scal; q.ids = ids; q.grad_fdc = grad; q.grad_expo = egrad;
+  q.edited = c->edited; q.G_pre = w.G_pre; q.scal = w.scal; q.ids = ids; q.grad_expo = egrad;
   dim3 g0(gridp(P, 256, 148 * 2), nb);
-  if (stage == 2) level0_kernel<0><<<g0, 256, 0, stream>>>(q); else level0_kernel<1><<<g0, 256, 0, stream>>>(q);
-  TCL_CHECK_LAUNCH("postopt(level0)");
-  if (stage == 2) pre_sink_kernel<0><<<g0, 256, 0, stream>>>(q); else pre_sink_kernel<1><<<g0, 256, 0, stream>>>(q);
-  TCL_CHECK_LAUNCH("postopt(pre_sink)");
+  if (stage == 2) {
+    if (w1) level0_uvt_kernel<true><<<g0, 256, 0, stream>>>(q, sh); else level0_uvt_kernel<false><<<g0, 256, 0, stream>>>(q, sh);
+    TCL_CHECK_LAUNCH("postopt(level0)");
+  } else {
+    level0_expo_kernel<<<g0, 256, 0, stream>>>(q);
+    TCL_CHECK_LAUNCH("postopt(level0)");
+    pre_sink_kernel<<<g0, 256, 0, stream>>>(q);
+    TCL_CHECK_LAUNCH("postopt(pre_sink)");
+  }
   // 7. Adam (+ loss assembly)
   LossAsm la;
   la.scal = w.scal; la.loss_out = loss_out;
@@ -901,17 +1128,21 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
   la.ms_share = (float)planes / (float)planes_g;
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
-  if (!do_adam) {
-    // gradient only (data parallel: the caller all-reduces grad, then calls tcl_adam_step): n = 0 elements,
-    // the single block just assembles this rank's share of the loss
+  if (!do_adam || stage == 2) {
+    // loss assembly only (n = 0 elements): gradient-only calls, and stage 2 whose Adam runs in adam_uvt_kernel
     adam_kernel<<<1, 32, 0, stream>>>(nullptr, nullptr, nullptr, nullptr, 0, 0.f, beta1, beta2, eps, 1.f, 1.f, la);
-  } else if (stage == 2) {
-    adam_uvt_kernel<<<gridp(U / 4 + 1, 256, 148 * 16), 256, 0, stream>>>(fdc, grad, m, v, U, lr, beta1, beta2, eps, bc1, bc2_sqrt);
-    TCL_CHECK_LAUNCH("postopt adam");
-    adam_kernel<<<1, 32, 0, stream>>>(nullptr, nullptr, nullptr, nullptr, 0, 0.f, beta1, beta2, eps, 1.f, 1.f, la);   // loss assembly
+    TCL_CHECK_LAUNCH("postopt(loss)");
+    if (do_adam) {
+      const long long rows = shards->rows_per_rank;
+      adam_uvt_kernel<<<gridp(rows / 4 + 1, 256, 148 * 16), 256, 0, stream>>>(shards->fdc[shards->rank], shards->grad[shards->rank], m, v,
+                                                                             rows, lr, beta1, beta2, eps, bc1, bc2_sqrt);
+      TCL_CHECK_LAUNCH("postopt(adam)");
+    }
+  } else {
+    adam_kernel<<<gridp((long long)c->N * 12, 256), 256, 0, stream>>>(expo, egrad, em, ev, (long long)c->N * 12, lr, beta1, beta2, eps,
+                                                                      bc1, bc2_sqrt, la);
+    TCL_CHECK_LAUNCH("postopt(adam)");
   }
-  else adam_kernel<<<gridp((long long)c->N * 12, 256), 256, 0, stream>>>(expo, egrad, em, ev, (long long)c->N * 12, lr, beta1, beta2, eps, bc1, bc2_sqrt, la);
-  TCL_CHECK_LAUNCH("postopt(adam)");
   return TCL_OK;
 }
 
@@ -919,16 +1150,19 @@ extern "C" int tcl_uvt_iteration(const tcl_postopt_ctx* ctx, const int* idx_host
                                  float* fdc, float* grad, float* m, float* v, float lr, float beta1, float beta2, float eps,
                                  int step, float* loss_out, cudaStream_t stream) {
   TCL_CHECK_ARG(ids && fdc && grad && m && v && U > 0, "tcl_uvt_iteration: null pointer");
-  return run_iteration(2, ctx, idx_host, n_batch, ids, U, fdc, grad, m, v, nullptr, nullptr, nullptr, nullptr, lr, beta1, beta2, eps,
-                       step, loss_out, stream);
+  tcl_uvt_shards s;
+  memset(&s, 0, sizeof(s));
+  s.world = 1; s.rank = 0; s.rows_per_rank = U; s.fdc[0] = fdc; s.grad[0] = grad;
+  return run_iteration(2, ctx, idx_host, n_batch, ids, &s, m, v, nullptr, nullptr, nullptr, nullptr, lr, beta1, beta2, eps,
+                       step, loss_out, stream, true);
 }
 
 extern "C" int tcl_exposure_iteration(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, float* exposure, float* grad,
                                       float* m, float* v, float lr, float beta1, float beta2, float eps, int step,
                                       float* loss_out, cudaStream_t stream) {
   TCL_CHECK_ARG(exposure && grad && m && v, "tcl_exposure_iteration: null pointer");
-  return run_iteration(1, ctx, idx_host, n_batch, nullptr, 0, nullptr, nullptr, nullptr, nullptr, exposure, grad, m, v, lr, beta1,
-                       beta2, eps, step, loss_out, stream);
+  return run_iteration(1, ctx, idx_host, n_batch, nullptr, nullptr, nullptr, nullptr, exposure, grad, m, v, lr, beta1,
+                       beta2, eps, step, loss_out, stream, true);
 }
 
 extern "C" int tcl_uvt_init(const float* edited, const int* ids, int N, int H, int W, long long U, float* fdc, float* cnt_ws,
@@ -960,47 +1194,22 @@ extern "C" int tcl_exposure_bake(float* edited, const float* exposure, int N, in
   return TCL_OK;
 }
 
-// Kernel-level test hooks (used by tests/test_postopt_gpu.py): one SSIM level in isolation.
-//   X, Y : [planes, h, w] fp32 (Y is indexed as frame = plane/3, channel = plane%3)
-//   sums : [planes][2] (cs sum, ssim sum) accumulated;  dX = d( sum_planes coef[p] * sum_map )/dX
-extern "C" int tcl_debug_ssim_level(const float* X, const float* Y, int planes, int h, int w, const float* coef, int use_ssim,
-                                    float* sums, float* dX, cudaStream_t stream) {
-  TCL_CHECK_ARG(X && Y && planes > 0 && planes % 3 == 0 && planes / 3 <= MAXB && h >= 11 && w >= 11, "tcl_debug_ssim_level: args");
-  int rc = ensure_gauss();
+// ---- data-parallel stage 2: the UVT rows and their gradient are sharded by row range across the ranks
+// of one NVSwitch box; every rank runs its slice of the batch, gathers rows with (peer) loads and scatters gradients with
+// (peer) reductions inside the same kernels, and after a cross-rank barrier applies Adam to its own shard only ----
+extern "C" int tcl_uvt_gradient_sharded(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, const int* ids,
+                                        const tcl_uvt_shards* shards, float* loss_out, cudaStream_t stream) {
+  TCL_CHECK_ARG(ids != nullptr, "tcl_uvt_gradient_sharded: null pointer");
+  int rc = check_shards(shards, "tcl_uvt_gradient_sharded");
   if (rc) return rc;
-  Batch bt; bt.n = planes / 3;
-  for (int i = 0; i < MAXB; ++i) bt.idx[i] = i < bt.n ? i : 0;
-  const float C1 = 1e-4f, C2 = 9e-4f;
-  const long long hw = (long long)h * w;
-  if (sums) {
-    cudaMemsetAsync(sums, 0, sizeof(float) * planes * 2, stream);
-    dim3 grid((w - 10 + ST - 1) / ST, (h - 10 + ST - 1) / ST, planes);
-    ssim_fwd_kernel<<<grid, 256, 0, stream>>>(X, hw, Y, 3 * hw, hw, bt, h, w, C1, C2, sums);
-    TCL_CHECK_LAUNCH("tcl_debug_ssim_level(fwd)");
-  }
-  if (dX) {
-    TCL_CHECK_ARG(coef != nullptr, "tcl_debug_ssim_level: coef");
-    const size_t bwd_smem = sizeof(float) * (2 * BR * BR + 5 * BP * BR + 3 * BP * BP);
-    cudaFuncSetAttribute(ssim_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem);
-    dim3 grid((w + BT - 1) / BT, (h + BT - 1) / BT, planes);
-    ssim_bwd_kernel<<<grid, 256, bwd_smem, stream>>>(X, hw, Y, 3 * hw, hw, bt, h, w, C1, C2, coef, use_ssim, nullptr, 0, 0, 0, 0, 0, dX, hw);
-    TCL_CHECK_LAUNCH("tcl_debug_ssim_level(bwd)");
-  }
-  return TCL_OK;
-}
-
-// ---- data-parallel variants: gradient accumulation only, then a separate Adam step ----
-extern "C" int tcl_uvt_gradient(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, const int* ids, long long U,
-                                const float* fdc, float* grad, float* loss_out, cudaStream_t stream) {
-  TCL_CHECK_ARG(ids && fdc && grad && U > 0, "tcl_uvt_gradient: null pointer");
-  return run_iteration(2, ctx, idx_host, n_batch, ids, U, const_cast<float*>(fdc), grad, nullptr, nullptr, nullptr, nullptr, nullptr,
-                       nullptr, 0.f, 0.9f, 0.999f, 1e-15f, 1, loss_out, stream, false);
+  return run_iteration(2, ctx, idx_host, n_batch, ids, shards, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.9f,
+                       0.999f, 1e-15f, 1, loss_out, stream, false);
 }
 
 extern "C" int tcl_exposure_gradient(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, const float* exposure, float* grad,
                                      float* loss_out, cudaStream_t stream) {
   TCL_CHECK_ARG(exposure && grad, "tcl_exposure_gradient: null pointer");
-  return run_iteration(1, ctx, idx_host, n_batch, nullptr, 0, nullptr, nullptr, nullptr, nullptr, const_cast<float*>(exposure), grad,
+  return run_iteration(1, ctx, idx_host, n_batch, nullptr, nullptr, nullptr, nullptr, const_cast<float*>(exposure), grad,
                        nullptr, nullptr, 0.f, 0.9f, 0.999f, 1e-8f, 1, loss_out, stream, false);
 }
 
@@ -1016,7 +1225,7 @@ extern "C" int tcl_adam_step(float* p, float* grad, float* m, float* v, long lon
   return TCL_OK;
 }
 
-// Data-parallel stage 2: Adam over the UVT rows after the [U,4] gradient has been all-reduced.
+// Adam over a UVT row shard: fdc, m, v are [rows,3], grad4 the [rows,4] gradient; leaves the gradient zeroed.
 extern "C" int tcl_adam_step_uvt(float* fdc, float* grad4, float* m, float* v, long long U, float lr, float beta1, float beta2,
                                  float eps, int step, cudaStream_t stream) {
   TCL_CHECK_ARG(fdc && grad4 && m && v && U > 0 && step >= 1, "tcl_adam_step_uvt: args");

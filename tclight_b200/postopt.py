@@ -115,31 +115,144 @@ def _shard_info(gen):
 
 def shard_batch(idxs, rank: int, world: int):
     """This rank's slice of a batch (round robin) plus the global normalisers: every rank draws the same
-    batches (same CPU RNG seed), processes idxs[rank::world], and the loss means stay global."""
+    batches (same CPU RNG state, see _sync_cpu_rng), processes idxs[rank::world], and the loss means stay global."""
     lst = [int(i) for i in idxs]
     return lst[rank::world], len(lst), sum(1 for i in lst if i > 0)
 
 
-def _dp_iteration(stage, ctx, mine, n_global, n_valid_global, params, grad, m, v, ids, U, lr, eps, step, loss_row):
-    """Gradient on the local slice with global normalisers -> all-reduce -> identical Adam on every rank."""
+def _sync_cpu_rng(device):
+    """Data parallel: every rank must draw the same DataLoader permutations, but the global CPU RNG has diverged by
+    now (get_chunks(shard_len) consumes a length-dependent amount of it in the sharded denoising passes).  Rank 0's
+    state is broadcast and adopted by all ranks, so the DP run consumes RNG exactly as rank 0 / a single-GPU run does."""
+    import torch.distributed as dist
+
+    st = torch.get_rng_state().to(device)
+    dist.broadcast(st, src=0)
+    torch.set_rng_state(st.cpu())
+
+
+class _PeerBuffer:
+    """A zero-filled device allocation of its own (tcl_peer_alloc) that other ranks of the box can map; exposes the
+    CUDA array interface so the owner can view it as a torch tensor."""
+
+    def __init__(self, nbytes: int):
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        check(lib.tcl_peer_alloc(nbytes, C.byref(ptr), handle), "tcl_peer_alloc")
+        self.ptr, self.nbytes, self.handle = ptr.value, nbytes, handle.raw
+
+    def view_f32(self, offset_bytes: int, numel: int, device) -> torch.Tensor:
+        holder = type("_Span", (), {})()
+        holder.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (self.ptr + offset_bytes, False),
+                                           "version": 2}
+        holder._keep = self
+        return torch.as_tensor(holder, device=device)
+
+    def free(self):
+        if self.ptr:
+            check(lib.tcl_peer_free(self.ptr), "tcl_peer_free")
+            self.ptr = None
+
+
+class UvtShardTable:
+    """The UVT rows [U,3] and their gradient [U,4] sharded by row range over the ranks of one box, every shard mapped
+    into every rank (tcl_uvt_shards in include/tclight.h).  Layout of one rank's buffer:
+    fdc [rows,3] | grad [rows,4] | barrier slots int32[TCL_MAX_RANKS]."""
+
+    def __init__(self, U: int, rank: int, world: int, device):
+        import torch.distributed as dist
+
+        self.U, self.rank, self.world, self.device = U, rank, world, device
+        rows = (((U + world - 1) // world) + 3) // 4 * 4
+        self.rows = max(rows, 256)
+        self._grad_off = self.rows * 12
+        self._flag_off = self.rows * 28
+        torch.cuda.synchronize(device)
+        self.buf = _PeerBuffer(self._flag_off + 4 * L.TCL_MAX_RANKS)
+        handles = [None] * world
+        dist.all_gather_object(handles, self.buf.handle)
+        self._mapped = []
+        bases = []
+        for r in range(world):
+            if r == rank:
+                bases.append(self.buf.ptr)
+                continue
+            base = C.c_void_p()
+            check(lib.tcl_ipc_open(handles[r], C.byref(base)), "tcl_ipc_open")
+            self._mapped.append(base.value)
+            bases.append(base.value)
+        t = L.UvtShards()
+        t.world, t.rank, t.rows_per_rank = world, rank, self.rows
+        self._flags = (C.c_void_p * world)()
+        for r, bptr in enumerate(bases):
+            t.fdc[r], t.grad[r], self._flags[r] = bptr, bptr + self._grad_off, bptr + self._flag_off
+        self.c = t
+        self.fdc_local = self.buf.view_f32(0, self.rows * 3, device).view(self.rows, 3)
+        self.grad_local = self.buf.view_f32(self._grad_off, self.rows * 4, device).view(self.rows, 4)
+        self._epoch = 0
+        dist.barrier()          # every rank has mapped every shard before anyone touches one
+
+    def barrier(self):
+        self._epoch += 1
+        check(lib.tcl_peer_barrier(self._flags, self.world, self.rank, self._epoch, stream_ptr()), "tcl_peer_barrier")
+
+    def load_full(self, fdc_full: torch.Tensor):
+        """Copy this rank's row range out of a full [U,3] table."""
+        lo = self.rank * self.rows
+        hi = min(lo + self.rows, self.U)
+        if hi > lo:
+            self.fdc_local[:hi - lo].copy_(fdc_full[lo:hi])
+
+    def gather_full(self) -> torch.Tensor:
+        """All shards -> a full [U,3] table on every rank (once, for the final render)."""
+        import torch.distributed as dist
+
+        full = torch.empty((self.world * self.rows, 3), device=self.device, dtype=torch.float32)
+        dist.all_gather_into_tensor(full, self.fdc_local.contiguous())
+        return full[:self.U].contiguous()
+
+    def close(self):
+        import torch.distributed as dist
+
+        torch.cuda.synchronize(self.device)
+        n_to = lib.tcl_peer_barrier_timeouts()
+        dist.barrier()
+        for bptr in self._mapped:
+            check(lib.tcl_ipc_close(bptr), "tcl_ipc_close")
+        self._mapped = []
+        dist.barrier()          # nobody still maps this rank's buffer
+        self.fdc_local = self.grad_local = None
+        self.buf.free()
+        if n_to:
+            raise TclError(f"tcl_peer_barrier timed out {n_to} time(s): the ranks did not run the same iterations")
+
+
+def _dp_exposure_iteration(ctx, mine, n_global, n_valid_global, params, grad, m, v, lr, step, loss_row):
+    """Stage 1: gradient on the local slice with global normalisers -> all-reduce of the [N,12] gradient -> identical
+    Adam on every rank."""
     import torch.distributed as dist
 
     ctx.c.norm_batch, ctx.c.norm_valid = n_global, n_valid_global
     if mine:
         arr, nb = _idx_array(mine)
-        if stage == 2:
-            check(lib.tcl_uvt_gradient(C.byref(ctx.c), arr, nb, ids.data_ptr(), U, params.data_ptr(), grad.data_ptr(),
-                                       loss_row.data_ptr(), stream_ptr()), "tcl_uvt_gradient")
-        else:
-            check(lib.tcl_exposure_gradient(C.byref(ctx.c), arr, nb, params.data_ptr(), grad.data_ptr(), loss_row.data_ptr(),
-                                            stream_ptr()), "tcl_exposure_gradient")
+        check(lib.tcl_exposure_gradient(C.byref(ctx.c), arr, nb, params.data_ptr(), grad.data_ptr(), loss_row.data_ptr(),
+                                        stream_ptr()), "tcl_exposure_gradient")
     dist.all_reduce(grad)
-    if stage == 2:
-        check(lib.tcl_adam_step_uvt(params.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), U, lr, 0.9, 0.999, eps,
-                                    step, stream_ptr()), "tcl_adam_step_uvt")
-    else:
-        check(lib.tcl_adam_step(params.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), params.numel(), lr, 0.9, 0.999,
-                                eps, step, stream_ptr()), "tcl_adam_step")
+    check(lib.tcl_adam_step(params.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), params.numel(), lr, 0.9, 0.999,
+                            1e-8, step, stream_ptr()), "tcl_adam_step")
+
+
+def _dp_uvt_iteration(ctx, tab: UvtShardTable, mine, n_global, n_valid_global, m, v, ids, lr, step, loss_row):
+    """Stage 2: gather / scatter against the row shards over peer memory, barrier, Adam on the local shard, barrier."""
+    ctx.c.norm_batch, ctx.c.norm_valid = n_global, n_valid_global
+    if mine:
+        arr, nb = _idx_array(mine)
+        check(lib.tcl_uvt_gradient_sharded(C.byref(ctx.c), arr, nb, ids.data_ptr(), C.byref(tab.c), loss_row.data_ptr(),
+                                           stream_ptr()), "tcl_uvt_gradient_sharded")
+    tab.barrier()
+    check(lib.tcl_adam_step_uvt(tab.fdc_local.data_ptr(), tab.grad_local.data_ptr(), m.data_ptr(), v.data_ptr(), tab.rows, lr,
+                                0.9, 0.999, 1e-15, step, stream_ptr()), "tcl_adam_step_uvt")
+    tab.barrier()
 
 
 def _idx_array(idxs) -> Tuple[C.Array, int]:
@@ -163,6 +276,8 @@ def exposure_align(gen) -> Tuple[torch.Tensor, List[float]]:
     n_it = gen.epochs_exposure * ((N + Bo - 1) // Bo)
     losses = torch.zeros((max(n_it, 1), 3), device=dev, dtype=torch.float32)
     step = 0
+    if world > 1:
+        _sync_cpu_rng(dev)
     loader = batch_iterator(N, Bo)
     for epoch in range(gen.epochs_exposure):
         for i, idxs in enumerate(loader):
@@ -171,7 +286,7 @@ def exposure_align(gen) -> Tuple[torch.Tensor, List[float]]:
             step += 1
             if world > 1:
                 mine, ng, nv = shard_batch(idxs, rank, world)
-                _dp_iteration(1, ctx, mine, ng, nv, exposure, grad, m, v, None, 0, lr, 1e-8, step, losses[step - 1])
+                _dp_exposure_iteration(ctx, mine, ng, nv, exposure, grad, m, v, lr, step, losses[step - 1])
                 continue
             arr, nb = _idx_array(idxs)
             check(lib.tcl_exposure_iteration(C.byref(ctx.c), arr, nb, exposure.data_ptr(), grad.data_ptr(), m.data_ptr(),
@@ -208,8 +323,17 @@ def unique_tensor_optimization(gen) -> Tuple[torch.Tensor, List[float]]:
     check(lib.tcl_uvt_init(ds.edited_images.data_ptr(), ids.data_ptr(), N, H, W, U, fdc.data_ptr(), cnt.data_ptr(), stream_ptr()),
           "tcl_uvt_init")
     del cnt
-    m, v = torch.zeros_like(fdc), torch.zeros_like(fdc)
-    grad = torch.zeros((U, 4), device=dev, dtype=torch.float32)     # {dR, dG, dB, pad}: one 16-byte reduction per scatter
+    tab = None
+    if world > 1:
+        tab = UvtShardTable(U, rank, world, dev)
+        tab.load_full(fdc)
+        del fdc
+        m, v = torch.zeros((tab.rows, 3), device=dev), torch.zeros((tab.rows, 3), device=dev)
+        _sync_cpu_rng(dev)
+        tab.barrier()
+    else:
+        m, v = torch.zeros_like(fdc), torch.zeros_like(fdc)
+        grad = torch.zeros((U, 4), device=dev, dtype=torch.float32)     # {dR, dG, dB, pad}: one 16-byte reduction per scatter
     n_it = gen.epochs * ((N + Bo - 1) // Bo)
     losses = torch.zeros((n_it, 3), device=dev, dtype=torch.float32)
     step = 0
@@ -219,7 +343,7 @@ def unique_tensor_optimization(gen) -> Tuple[torch.Tensor, List[float]]:
             step += 1
             if world > 1:
                 mine, ng, nv = shard_batch(idxs, rank, world)
-                _dp_iteration(2, ctx, mine, ng, nv, fdc, grad, m, v, ids, U, feature_lr, 1e-15, step, losses[step - 1])
+                _dp_uvt_iteration(ctx, tab, mine, ng, nv, m, v, ids, feature_lr, step, losses[step - 1])
                 continue
             arr, nb = _idx_array(idxs)
             check(lib.tcl_uvt_iteration(C.byref(ctx.c), arr, nb, ids.data_ptr(), U, fdc.data_ptr(), grad.data_ptr(), m.data_ptr(),
@@ -228,6 +352,8 @@ def unique_tensor_optimization(gen) -> Tuple[torch.Tensor, List[float]]:
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(losses)
+        fdc = tab.gather_full()
+        tab.close()
     images = torch.empty((N, 3, H, W), device=dev, dtype=torch.float32)
     check(lib.tcl_uvt_render(fdc.data_ptr(), ids.data_ptr(), N, H, W, images.data_ptr(), stream_ptr()), "tcl_uvt_render")
     gen._features_dc = fdc
@@ -292,8 +418,16 @@ def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: i
     cnt = torch.empty(U, device=device, dtype=torch.float32)
     check(lib.tcl_uvt_init(ds.edited_images.data_ptr(), ids.data_ptr(), N, H, W, U, fdc.data_ptr(), cnt.data_ptr(), stream_ptr()), "tcl_uvt_init")
     del cnt
-    m, v = torch.zeros_like(fdc), torch.zeros_like(fdc)
-    grad = torch.zeros((U, 4), device=device, dtype=torch.float32)
+    tab = None
+    if world > 1:
+        tab = UvtShardTable(U, rank, world, device)
+        tab.load_full(fdc)
+        del fdc
+        m, v = torch.zeros((tab.rows, 3), device=device), torch.zeros((tab.rows, 3), device=device)
+        tab.barrier()
+    else:
+        m, v = torch.zeros_like(fdc), torch.zeros_like(fdc)
+        grad = torch.zeros((U, 4), device=device, dtype=torch.float32)
     losses = torch.zeros((iters + 8, 3), device=device)
     gcpu = torch.Generator().manual_seed(0)
     lr = 0.05 * Bo / N
@@ -304,7 +438,7 @@ def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: i
             row = losses[(step0 + i) % len(losses)]
             if world > 1:
                 mine, ng, nv = shard_batch(idxs, rank, world)
-                _dp_iteration(2, ctx, mine, ng, nv, fdc, grad, m, v, ids, U, lr, 1e-15, step0 + i + 1, row)
+                _dp_uvt_iteration(ctx, tab, mine, ng, nv, m, v, ids, lr, step0 + i + 1, row)
                 continue
             arr, nb = _idx_array(idxs)
             check(lib.tcl_uvt_iteration(C.byref(ctx.c), arr, nb, ids.data_ptr(), U, fdc.data_ptr(), grad.data_ptr(), m.data_ptr(),
@@ -329,6 +463,7 @@ def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: i
         import torch.distributed as dist
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(losses)
+        tab.close()
     ms = ms_t.item()
     P_ = H * W
     alg_bytes = 80.0 * Bo * P_ + 84.0 * U
@@ -343,5 +478,6 @@ def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: i
             "U": U, "U_over_NP": U / (N * P_), "algorithmic_bytes_per_iter": alg_bytes,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": kind, "unit": "GB/s", "frac": ach / peak, "traffic": None},
             "loss_first_last": [losses[3, 0].item(), losses[(3 + iters - 1) % len(losses), 0].item()], "n_gpus": world,
-            "parallelism": f"batch-parallel x{world}, NCCL all-reduce of the [U,3] gradient" if world > 1 else "single GPU",
+            "parallelism": (f"batch-parallel x{world}; UVT rows + gradient sharded by row range, gathered / reduced through peer memory over "
+                            "NVLink inside the gather and level-0 kernels, Adam on the local shard") if world > 1 else "single GPU",
             "note": "dense-Adam semantics (every UVT row updated every iteration, as torch.optim.Adam does)"}

@@ -1,6 +1,8 @@
-"""2-GPU parity check of the data-parallel optimiser (not collected by pytest; run on a 2-GPU box:
+"""2-GPU parity check of the data-parallel optimiser (launched by tests/test_dp_postopt_2gpu.py, or by hand on a 2-GPU box:
 `python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dp_postopt_check_2gpu.py`); every rank runs the DP
-path, rank 0 also runs the single-GPU path and the oracle and compares losses / images."""
+path (stage 2: UVT rows sharded over peer memory; stage 1: all-reduced exposure gradient), rank 0 also runs the single-GPU path
+and compares losses / images.  N = 7 frames over 2 ranks (N % world != 0), and the ranks' CPU RNGs are deliberately driven apart
+before each stage, as the sharded denoising passes do (get_chunks consumes a shard-length-dependent amount of RNG)."""
 import os, sys, types
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
@@ -22,6 +24,8 @@ def mk(ds, inv, world_, rank_):
 edited, flows, masks, inv = O.synthetic_clip(n=7, h=176, w=192, seed=1, device=dev)
 for stage in (2, 1):
     torch.manual_seed(5)
+    if rank > 0:
+        torch.randperm(2 + rank)            # diverged CPU RNG on the other ranks
     ds = P.OptDataset(edited.clone(), flows, masks, device=dev)
     fn = P.unique_tensor_optimization if stage == 2 else P.exposure_align
     img_dp, loss_dp = fn(mk(ds, inv, world, rank))

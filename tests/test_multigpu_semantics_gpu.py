@@ -47,7 +47,8 @@ def oracle_sharded(dev, world, x, cc, conds, conds_t, n_timesteps, win):
                                         win_size_t=win, rng=[torch.Generator(device=dev).manual_seed(12345)] * len(x))
 
 
-@pytest.mark.parametrize("adt,tol", [(torch.float16, 1.5e-2), (torch.bfloat16, 6e-2)])
+# measured on the B200: fp16 5.6e-3, bf16 1.15e-2 (and the pool-reset oracle differs from the single-pool one by 5.9e-3)
+@pytest.mark.parametrize("adt,tol", [(torch.float16, 1.5e-2), (torch.bfloat16, 3e-2)])
 def test_two_emulated_ranks_match_pool_reset_oracle(cuda, adt, tol):
     from oracle import pipeline_ref as P
     from oracle.unet_ref import make_unet

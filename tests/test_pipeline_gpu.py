@@ -2,7 +2,7 @@
 generate.py:560-604): VAE encode -> multi-axis denoising with VidToMe -> VAE decode -> soft masks / flow ids / unique
 inverse -> exposure alignment -> unique-video-tensor optimisation, all on the B200 kernels with seeded random weights,
 against the same chain assembled from the oracle pieces.  The chain is long (16-bit UNet + VAE, discrete merge
-decisions), so the latent is held to rel-L2 <= 8e-2; the integer
+decisions); bounds are <= 3x the error measured on the B200; the integer
 parts (flow ids from identical inputs) stay bit-exact."""
 import numpy as np
 import pytest
@@ -61,15 +61,16 @@ def test_relight_end_to_end_vs_oracle_chain(cuda):
     lat = P.ddim_sample_oracle(ref_unet, x0, conds, conds_t, cc, n_timesteps=2, alpha_t=0.01, win_size_t=6, rng=rng)
     rel = ((info["latent"].float() - lat).norm() / lat.norm()).item()
     print(f"end-to-end latent rel-L2 vs oracle chain: {rel:.3e}")
-    assert rel < 8e-2
+    assert rel < 8e-3            # measured 2.6e-3
     dec = V.decode_latents(ref_vae, lat).clamp(0, 1)
     # integer part: identical inputs => identical ids (device masks fed to the oracle's id propagation)
     ids_ref = R.flow_ids(frames.cpu(), fwd.cpu(), info["mask_bwds"].cpu(), rgb_threshold=0.05)
     assert torch.equal(info["unq_inv"].cpu().view(N, H, W).to(torch.int32), ids_ref)
     # ---- the optimiser on the ORACLE's decoded frames (same DataLoader draws: the global CPU RNG has advanced
     # identically on both sides), so the FINAL frames are compared with the oracle chain's final frames ----
-    masks_ref = R.soft_mask_bwds(frames * 2 - 1, fwd, bwd, alpha=0.5)
-    inv_ref = R.unique_inverse(R.flow_ids(frames.cpu(), fwd.cpu(), masks_ref.cpu(), rgb_threshold=0.05)).to(cuda)
+    masks_ref = R.soft_mask_bwds((frames * 2 - 1).cpu(), fwd.cpu(), bwd.cpu(), alpha=0.5)
+    inv_ref = R.unique_inverse(R.flow_ids(frames.cpu(), fwd.cpu(), masks_ref, rgb_threshold=0.05)).to(cuda)
+    masks_ref = masks_ref.to(cuda)
     b1 = O.draw_batches(N, 4, 1)
     aligned, _, loss1 = O.stage1_exposure(dec.float(), bwd, masks_ref, b1)
     b2 = O.draw_batches(N, 4, 1)

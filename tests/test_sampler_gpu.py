@@ -4,7 +4,7 @@ generate.py in the build container) over the oracle UNet/scheduler, same seeds, 
 
 Tolerances: scheduler / AdaIN kernels reproduce the reference's 16-bit roundings => compared at
 <= 2 ulp-level (atol 2e-3 relative to unit-scale latents); full sampler (fp16 UNet vs fp32 oracle
-UNet over several steps with VidToMe) => rel-L2 <= 5e-2, reported."""
+UNet over several steps with VidToMe) => bounds <= 3x the measured error, per test."""
 import numpy as np
 import pytest
 import torch
@@ -106,9 +106,9 @@ def _inputs(cuda, N, h, w, seed=7):
 
 # Loop-level bounds are <= 3x the error measured on the B200 (recorded next to each bound); the discrete VidToMe
 # decisions make the error of a multi-step run heavy-tailed, so the measured value is printed for the record.
-@pytest.mark.parametrize("adt,tol", [(torch.float16, 1.5e-2), (torch.bfloat16, 6e-2)])
+@pytest.mark.parametrize("adt,tol", [(torch.float16, 1.5e-2), (torch.bfloat16, 3e-2)])
 def test_ddim_sample_multi_axis_vs_oracle(cuda, adt, tol):
-    """4 steps, 8 frames, multi-axis, VidToMe on, tiny widths.  Measured: fp16 5.0e-3, bf16 2.2e-2."""
+    """4 steps, 8 frames, multi-axis, VidToMe on, tiny widths.  Measured on the B200: fp16 5.0e-3, bf16 9.9e-3."""
     from oracle import pipeline_ref as P
 
     ref_unet, gen = _sampler_pair(cuda, adt, dict(block_out_channels=(64, 128, 256, 256), cross_attention_dim=768),
@@ -126,9 +126,9 @@ def test_ddim_sample_multi_axis_vs_oracle(cuda, adt, tol):
     assert err < tol
 
 
-@pytest.mark.parametrize("adt,tol", [(torch.float16, 1.5e-2), (torch.bfloat16, 6e-2)])
+@pytest.mark.parametrize("adt,tol", [(torch.float16, 1.5e-2), (torch.bfloat16, 2.5e-2)])
 def test_baseline_config1_sd15_widths(cuda, adt, tol):
-    """BASELINE.json configs[0] exactly: 8 frames, 256x256 (latent 32x32), 4 denoising steps, single axis,
+    """Measured on the B200: fp16 5.3e-3, bf16 8.6e-3.  BASELINE.json configs[0] exactly: 8 frames, 256x256 (latent 32x32), 4 denoising steps, single axis,
     **SD-1.5 widths** (320/640/1280/1280: ds-1 merging at head dim 40, ds-2 at head dim 80), VidToMe on, L = 154 —
     B200 path vs the oracle loop on the same seeds."""
     from oracle import pipeline_ref as P
@@ -147,9 +147,9 @@ def test_baseline_config1_sd15_widths(cuda, adt, tol):
     assert err < tol
 
 
-@pytest.mark.parametrize("adt,tol", [(torch.float16, 1.5e-2), (torch.bfloat16, 6e-2)])
+@pytest.mark.parametrize("adt,tol", [(torch.float16, 1.5e-2), (torch.bfloat16, 3e-2)])
 def test_multi_axis_step_sd15_widths(cuda, adt, tol):
-    """One full multi-axis step (xy pass + yt pass over 2 overlapping windows + AdaIN/blend + DPM-Solver++ update) at
+    """Measured on the B200: fp16 5.7e-3, bf16 9.9e-3.  Two full multi-axis steps (xy pass + yt pass over 2 overlapping windows + AdaIN/blend + DPM-Solver++ update) at
     SD-1.5 widths: the yt 'images' are (frames x height) = 6x32 per latent column."""
     from oracle import pipeline_ref as P
 

@@ -1,7 +1,7 @@
 """UNet-level GPU parity: UNetB200 (CUDA kernels, 16-bit) vs the oracle UNet (oracle/unet_ref.py,
 torch fp32 on the same device) with identical seeded weights.
 Tolerances: fp16 rel-L2 <= 2e-3 per fused op; accumulated over the ~60 layers
-of a forward we assert <= 1e-2 (fp16) / 4e-2 (bf16) on the final eps."""
+of a forward the bounds are <= 3x the error measured on the B200 (noted next to each assert)."""
 import pytest
 import torch
 
@@ -25,7 +25,7 @@ def _pair(cuda, dtype, **kw):
 TINY = dict(block_out_channels=(64, 128, 256, 256), cross_attention_dim=768)
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 4e-2)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 5e-3), (torch.bfloat16, 4e-2)])      # measured 1.7e-3 / 1.4e-2
 @pytest.mark.parametrize("h,w", [(16, 16), (12, 20)])
 def test_unet_tiny_unpatched(cuda, dtype, tol, h, w):
     ref, mine = _pair(cuda, dtype, **TINY)
@@ -66,17 +66,18 @@ def test_unet_sd15_width_unpatched(cuda):
     got = mine(sample.half(), t, encoder_hidden_states=ehs.half(), cross_attention_kwargs={"concat_conds": cc.half()}).sample
     err = rel_l2(got, want)
     print(f"sd15-width unet fp16 23x40: rel-L2 {err:.2e}")
-    assert err < 1e-2
+    assert err < 4e-3            # measured 1.4e-3
 
 
-def test_unet_tiny_vidtome(cuda):
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2.5e-2), (torch.bfloat16, 6e-2)])
+def test_unet_tiny_vidtome(cuda, dtype, tol):
     """With VidToMe patched on both sides.  Index selection is bit-exact only given equal node_max
     (tests/test_vidtome_gpu.py); against an fp32 oracle a few near-tied matches may differ, so the
     bound here is looser and the agreement is reported."""
     from oracle.unet_ref import apply_oracle_patch, reset_oracle_pool
     from tclight_b200 import vidtome
 
-    ref, mine = _pair(cuda, torch.float16, **TINY)
+    ref, mine = _pair(cuda, dtype, **TINY)
     apply_oracle_patch(ref)
     vidtome.apply_patch(mine, 0.6, True, 0.5, batch_size=2, align_batch=True, global_rand=0.5)
     torch.manual_seed(3)
@@ -92,7 +93,7 @@ def test_unet_tiny_vidtome(cuda):
         ehs = text.repeat_interleave(F, dim=0)
         t = torch.tensor(801, device=cuda)
         want = ref(sample, t, encoder_hidden_states=ehs, cross_attention_kwargs={"concat_conds": cc}).sample
-        got = mine(sample.half(), t, encoder_hidden_states=ehs.half(), cross_attention_kwargs={"concat_conds": cc.half()}).sample
+        got = mine(sample.to(dtype), t, encoder_hidden_states=ehs.to(dtype), cross_attention_kwargs={"concat_conds": cc.to(dtype)}).sample
         errs.append(rel_l2(got, want))
-    print("tiny unet + VidToMe rel-L2 per chunk:", ["%.2e" % e for e in errs])
-    assert max(errs) < 5e-2
+    print(f"tiny unet + VidToMe {dtype} rel-L2 per chunk:", ["%.2e" % e for e in errs])
+    assert max(errs) < tol       # measured fp16 8.8e-3
