@@ -345,21 +345,26 @@ __device__ __forceinline__ void shard_of(const Shards& sh, int id, int& owner, i
   owner = o; local = lo;
 }
 
-// stage 2: X = clamp(SH2RGB(fdc[id]), 0, 1); flags bit c = gradient passes (0 <= v <= 1).  One thread per 2x2 pixel
-// quad (8-byte id loads, 8-byte X stores); for the batch frames the quad mean is the level-1 pyramid value (avg_pool2d of
-// an even-sized image has no padding), written in the same pass when `xpyr1` is given.
+// X layout: one float4 per pixel, [2n][P] = {R, G, B, flags} with the three clamped channels and, in lane 3, the bits of
+// an int whose bit c says "the clamp passed the gradient of channel c" (0 <= v <= 1).  A bicubic tap, a TV neighbour or a
+// pixel's own value is then ONE 16-byte load, and the tap's clamp flags come with it.
+__device__ __forceinline__ float4 pack_px(float r, float g, float b, unsigned fl) { return make_float4(r, g, b, __uint_as_float(fl)); }
+
+// stage 2: X = clamp(SH2RGB(fdc[id]), 0, 1).  One thread per 2x2 pixel quad (8-byte id loads, 32-byte X stores); for the
+// batch frames the quad mean is the level-1 pyramid value (avg_pool2d of an even-sized image has no padding), written
+// in the same pass.
 template <bool W1>
 __global__ void __launch_bounds__(256)
-uvt_gather_quad_kernel(Shards sh, const int* __restrict__ ids, int H, int W, Batch bt, float* __restrict__ X,
-                       unsigned char* __restrict__ flags, float* __restrict__ xpyr1, long long pyr_plane_stride) {
+uvt_gather_quad_kernel(Shards sh, const int* __restrict__ ids, int H, int W, Batch bt, float4* __restrict__ X,
+                       float* __restrict__ xpyr1, long long pyr_plane_stride) {
   const int h2 = H >> 1, w2 = W >> 1;
   const long long P = (long long)H * W;
   const long long quads = (long long)h2 * w2;
   const long long total = (long long)2 * bt.n * quads;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int f = (int)(i / quads);
-    const long long qd = i - (long long)f * quads;
-    const int qy = (int)(qd / w2), qx = (int)(qd - (long long)qy * w2);
+    const int qd = (int)(i - (long long)f * quads);
+    const int qy = qd / w2, qx = qd - qy * w2;
     int fr = f < bt.n ? bt.idx[f] : bt.idx[f - bt.n] - 1;
     if (fr < 0) fr = 0;
     const long long p0 = (long long)(2 * qy) * W + 2 * qx;
@@ -367,7 +372,7 @@ uvt_gather_quad_kernel(Shards sh, const int* __restrict__ ids, int H, int W, Bat
     const int2 ib = *reinterpret_cast<const int2*>(ids + (long long)fr * P + p0 + W);
     const int id4[4] = {ia.x, ia.y, ib.x, ib.y};
     float val[4][3];
-    unsigned char fl[4];
+    unsigned fl[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       int owner, local;
@@ -381,24 +386,23 @@ uvt_gather_quad_kernel(Shards sh, const int* __restrict__ ids, int H, int W, Bat
         val[k][c] = fminf(fmaxf(v, 0.f), 1.f);
       }
     }
+    float4* dst = X + (long long)f * P + p0;
+    dst[0] = pack_px(val[0][0], val[0][1], val[0][2], fl[0]);
+    dst[1] = pack_px(val[1][0], val[1][1], val[1][2], fl[1]);
+    dst[W] = pack_px(val[2][0], val[2][1], val[2][2], fl[2]);
+    dst[W + 1] = pack_px(val[3][0], val[3][1], val[3][2], fl[3]);
+    if (f < bt.n) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float* dst = X + ((long long)f * 3 + c) * P + p0;
-      *reinterpret_cast<float2*>(dst) = make_float2(val[0][c], val[1][c]);
-      *reinterpret_cast<float2*>(dst + W) = make_float2(val[2][c], val[3][c]);
-      if (xpyr1 && f < bt.n)
+      for (int c = 0; c < 3; ++c)
         xpyr1[((long long)f * 3 + c) * pyr_plane_stride + (long long)qy * w2 + qx] =
             (val[0][c] + val[1][c] + val[2][c] + val[3][c]) * 0.25f;
     }
-    *reinterpret_cast<uchar2*>(flags + (long long)f * P + p0) = make_uchar2(fl[0], fl[1]);
-    *reinterpret_cast<uchar2*>(flags + (long long)f * P + p0 + W) = make_uchar2(fl[2], fl[3]);
   }
 }
 
-// odd image sizes: one thread per pixel, the pyramid is pooled by avgpool2_kernel afterwards
+// odd image sizes: one thread per pixel, level 1 is pooled by avgpool2_x4_kernel afterwards
 template <bool W1>
-__global__ void uvt_gather_kernel(Shards sh, const int* __restrict__ ids, long long P, Batch bt,
-                                  float* __restrict__ X, unsigned char* __restrict__ flags) {
+__global__ void uvt_gather_kernel(Shards sh, const int* __restrict__ ids, long long P, Batch bt, float4* __restrict__ X) {
   const long long total = (long long)2 * bt.n * P;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int f = (int)(i / P);
@@ -408,20 +412,21 @@ __global__ void uvt_gather_kernel(Shards sh, const int* __restrict__ ids, long l
     int owner, local;
     shard_of<W1>(sh, ids[(long long)fr * P + p], owner, local);
     const float* row = sh.fdc[owner] + (long long)local * 3;
-    unsigned char fl = 0;
+    unsigned fl = 0;
+    float val[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float v = row[c] * SH_C0 + 0.5f;
       if (v >= 0.f && v <= 1.f) fl |= (1u << c);
-      X[((long long)f * 3 + c) * P + p] = fminf(fmaxf(v, 0.f), 1.f);
+      val[c] = fminf(fmaxf(v, 0.f), 1.f);
     }
-    flags[i] = fl;
+    X[i] = pack_px(val[0], val[1], val[2], fl);
   }
 }
 
 // stage 1: X_j = clamp(sum_k in_k E[k][j] + E[j][3], 0, 1), E = exposure[frame] (3x4 row-major)
 __global__ void exposure_apply_kernel(const float* __restrict__ edited, const float* __restrict__ expo, long long P, Batch bt,
-                                      float* __restrict__ X, unsigned char* __restrict__ flags) {
+                                      float4* __restrict__ X) {
   const long long total = (long long)2 * bt.n * P;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int f = (int)(i / P);
@@ -431,19 +436,70 @@ __global__ void exposure_apply_kernel(const float* __restrict__ edited, const fl
     const float* E = expo + (long long)fr * 12;
     const float* src = edited + (long long)fr * 3 * P + p;
     const float in0 = src[0], in1 = src[P], in2 = src[2 * P];
-    unsigned char fl = 0;
+    unsigned fl = 0;
+    float val[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const float v = in0 * E[0 * 4 + j] + in1 * E[1 * 4 + j] + in2 * E[2 * 4 + j] + E[j * 4 + 3];
       if (v >= 0.f && v <= 1.f) fl |= (1u << j);
-      X[((long long)f * 3 + j) * P + p] = fminf(fmaxf(v, 0.f), 1.f);
+      val[j] = fminf(fmaxf(v, 0.f), 1.f);
     }
-    flags[i] = fl;
+    X[i] = pack_px(val[0], val[1], val[2], fl);
+  }
+}
+
+// level 0 -> level 1 of the batch frames' pyramid from the interleaved X (avg_pool2d, padding = size % 2)
+__global__ void avgpool2_x4_kernel(const float4* __restrict__ X, long long P, int hi, int wi, int ph, int pw,
+                                   float* __restrict__ out, long long out_stride, int ho, int wo, int frames) {
+  const long long total = (long long)frames * ho * wo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % wo);
+    const int oy = (int)((i / wo) % ho);
+    const int f = (int)(i / ((long long)wo * ho));
+    const float4* src = X + f * P;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int y = 2 * oy - ph + dy, x = 2 * ox - pw + dx;
+        if (y >= 0 && y < hi && x >= 0 && x < wi) { const float4 t = src[(long long)y * wi + x]; s0 += t.x; s1 += t.y; s2 += t.z; }
+      }
+    float* dst = out + (long long)f * 3 * out_stride + (long long)oy * wo + ox;
+    dst[0] = s0 * 0.25f; dst[out_stride] = s1 * 0.25f; dst[2 * out_stride] = s2 * 0.25f;
+  }
+}
+
+// d(loss)/dX at level 0 coming from MS-SSIM is the avg-pool backward chain of levels 1..4,
+//   dX_0 = 1/4 up(own_1 + 1/4 up(own_2 + 1/4 up(own_3 + 1/4 up(own_4))))     (up = nearest, with the pooling padding);
+// the bracket is evaluated once per level-1 pixel here (interleaved RGB, one 16-byte load per level-0 pixel later).
+__global__ void own_collapse_kernel(const float* __restrict__ own, long long own_stride, Pyr py, int frames, float4* __restrict__ out) {
+  const int h1 = py.h[1], w1 = py.w[1];
+  const long long total = (long long)frames * h1 * w1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x1 = (int)(i % w1);
+    const int y1 = (int)((i / w1) % h1);
+    const int f = (int)(i / ((long long)w1 * h1));
+    float g[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = own[((long long)f * 3 + c) * own_stride + py.off[1] + (long long)y1 * w1 + x1];
+    int y = y1, x = x1;
+    float wgt = 0.25f;
+#pragma unroll
+    for (int l = 2; l <= 4; ++l) {
+      y = (y + py.ph[l - 1]) >> 1;
+      x = (x + py.pw[l - 1]) >> 1;
+      if (y >= py.h[l] || x >= py.w[l]) break;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) g[c] += wgt * own[((long long)f * 3 + c) * own_stride + py.off[l] + (long long)y * py.w[l] + x];
+      wgt *= 0.25f;
+    }
+    out[i] = make_float4(0.25f * g[0], 0.25f * g[1], 0.25f * g[2], 0.f);
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// fused level-0 kernel over the batch frames
+// fused level-0 kernels over the batch frames
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float cubic1(float x) { const float A = -0.75f; return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
 __device__ __forceinline__ float cubic2(float x) { const float A = -0.75f; return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
@@ -459,15 +515,13 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 struct L0Params {
   int H, W;
-  long long P;
+  int P;
   Batch bt;
-  const float* X;                 // [2n,3,P]
-  const unsigned char* flags;     // [2n,P]
+  const float4* X;                // [2n][P] {R,G,B,flags}
   const float* flows;             // [N,2,P]
   const float* mask;              // [N,1,P]
-  const float* own;               // per-level MS-SSIM gradients [n*3 planes][pyramid] (ssim_bwd_all_kernel)
-  long long own_stride;
-  Pyr py;
+  const float4* own1;             // [n][h1*w1] collapsed MS-SSIM gradient at level-1 resolution (own_collapse_kernel)
+  int h1, w1, ph0, pw0;
   float k_flow;                   // lambda_flow / (n_valid*3*P)
   float k_tvh, k_tvw;             // lambda_tv*2/(count_h*n), lambda_tv*2/(count_w*n)
   float k_l1;                     // stage 1: (1-lambda_flow)*(1-lambda_dssim)/(n*3*P); 0 in stage 2
@@ -475,32 +529,18 @@ struct L0Params {
   float* G_pre;                   // stage 1: [n,P,4] atomically accumulated predecessor gradient (lane 3 unused)
   float* scal;
   // sinks
-  const int* ids;                         // stage 2: unq_inv [N*P]
-  float* grad_expo;                       // stage 1: [N,12]
+  const int* ids;                 // stage 2: unq_inv [N*P]
+  float* grad_expo;               // stage 1: [N,12]
 };
-
-// d(loss)/dX at level 0 coming from MS-SSIM: the avg-pool backward chain of levels 1..4
-//   dX_0 = 1/4 up(own_1 + 1/4 up(own_2 + 1/4 up(own_3 + 1/4 up(own_4))))     (up = nearest, with the pooling padding)
-__device__ __forceinline__ float msssim_grad(const float* __restrict__ own_plane, const Pyr& py, int y, int x) {
-  float g = 0.f, wgt = 0.25f;
-#pragma unroll
-  for (int l = 1; l <= 4; ++l) {
-    y = (y + py.ph[l - 1]) >> 1;
-    x = (x + py.pw[l - 1]) >> 1;
-    if (y >= py.h[l] || x >= py.w[l]) break;
-    g += wgt * own_plane[py.off[l] + (long long)y * py.w[l] + x];
-    wgt *= 0.25f;
-  }
-  return g;
-}
 
 struct Bicubic {
   float cx[4], cy[4];
   int x0, y0;
 };
-__device__ __forceinline__ void bicubic_setup(const L0Params& q, int fr, long long p, int x, int y, Bicubic& bc) {
-  const float fx = q.flows[((long long)fr * 2 + 0) * q.P + p] + (float)x;
-  const float fy = q.flows[((long long)fr * 2 + 1) * q.P + p] + (float)y;
+__device__ __forceinline__ void bicubic_setup(const L0Params& q, int fr, int p, int x, int y, Bicubic& bc) {
+  const float* fl = q.flows + (long long)fr * 2 * q.P + p;
+  const float fx = fl[0] + (float)x;
+  const float fy = fl[q.P] + (float)y;
   const float gx = (fx / (float)(q.W - 1) - 0.5f) * 2.f;
   const float gy = (fy / (float)(q.H - 1) - 0.5f) * 2.f;
   const float ix = ((gx + 1.f) / 2.f) * (float)(q.W - 1);
@@ -510,67 +550,86 @@ __device__ __forceinline__ void bicubic_setup(const L0Params& q, int fr, long lo
   cubic_coeffs(iy - fy0, bc.cy);
   bc.x0 = (int)fx0 - 1; bc.y0 = (int)fy0 - 1;
 }
-__device__ __forceinline__ void bicubic_sample(const L0Params& q, const float* __restrict__ Xp, const Bicubic& bc, float (&wv)[3]) {
+// 16 taps of 16 bytes; tf[j>>1] collects the taps' clamp flags, 3 bits per tap at bit 3*(4*(j&1)+i) (0 for taps outside
+// the image: they carry no gradient either)
+__device__ __forceinline__ void bicubic_sample(const L0Params& q, const float4* __restrict__ Xp, const Bicubic& bc, float (&wv)[3],
+                                               unsigned (&tf)[2]) {
   wv[0] = wv[1] = wv[2] = 0.f;
+  tf[0] = tf[1] = 0u;
+  const bool inx = bc.x0 >= 0 && bc.x0 + 3 < q.W;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int yy = bc.y0 + j;
     if (yy < 0 || yy >= q.H) continue;
+    const float4* rowp = Xp + (yy * q.W + bc.x0);
     float row[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int xx = bc.x0 + i;
-      if (xx < 0 || xx >= q.W) continue;
-      const long long o = (long long)yy * q.W + xx;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) row[c] += Xp[c * q.P + o] * bc.cx[i];
+      if (!inx && (bc.x0 + i < 0 || bc.x0 + i >= q.W)) continue;
+      const float4 t = __ldg(rowp + i);
+      row[0] += t.x * bc.cx[i]; row[1] += t.y * bc.cx[i]; row[2] += t.z * bc.cx[i];
+      tf[j >> 1] |= (__float_as_uint(t.w) & 7u) << (3 * (4 * (j & 1) + i));
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) wv[c] += row[c] * bc.cy[j];
   }
 }
+__device__ __forceinline__ unsigned tap_flags(const unsigned (&tf)[2], int j, int i) { return (tf[j >> 1] >> (3 * (4 * (j & 1) + i))) & 7u; }
 
 // ------------------------------------------------------------------------------------------
-// Stage 2, fused level-0 kernel: bicubic flow warp forward + backward, masked L1, TV, MS-SSIM gradient chain, and the
-// gradient sinks — every pixel's dLoss/dX goes straight into the UVT gradient row of its id (local or peer shard).
-// The bicubic backward would be 16 reductions per pixel; instead the four taps of a row are summed across the warp
-// first: neighbouring pixels of a smooth flow hit neighbouring columns, so tap i of lane l and tap i-1 of lane l+1 land
-// on the same predecessor pixel.  The partial sums travel one lane to the right per stage (3 shuffles per channel and
-// row) and a lane only issues a reduction where its chain ends: ~1 reduction per pixel and row instead of 4.
+// Stage 2, fused level-0 kernel: bicubic flow warp forward + backward, masked L1, TV, MS-SSIM gradient, and the gradient
+// sinks — every pixel's dLoss/dX goes straight into the UVT gradient row of its id (local or peer shard).
+//
+// The bicubic backward is 16 contributions per pixel.  A warp walks 29 consecutive pixels of one image row (lanes 3..31;
+// lanes 0..2 re-evaluate the three pixels before them as helpers).  For a smooth flow neighbouring pixels hit neighbouring
+// columns: tap i of lane l and tap 0 of lane l+i land on the same predecessor pixel, so lane m sums
+// v0(m) + v1(m-1) + v2(m-2) + v3(m-3) with three independent shuffles per channel and row and issues ONE 16-byte
+// reduction per row into the predecessor pixel's UVT row — 4 instead of 16 per pixel.  Where the chain is broken (flow
+// discontinuity, image border) the producer reduces the tap itself; taps whose consumer lies in the next segment are left to
+// that segment's helper lanes.
 // ------------------------------------------------------------------------------------------
+constexpr int SEG = 29;
 template <bool W1>
 __global__ void __launch_bounds__(256)
 level0_uvt_kernel(L0Params q, Shards sh) {
   __shared__ float red[3][8];
   const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int fr = q.bt.idx[b];
   const bool valid = fr > 0;
-  const float* Xi = q.X + (long long)b * 3 * q.P;
-  const float* Xp = q.X + (long long)(q.bt.n + b) * 3 * q.P;
-  const unsigned char* fl_pre = q.flags + (long long)(q.bt.n + b) * q.P;
+  const float4* Xi = q.X + (long long)b * q.P;
+  const float4* Xp = q.X + (long long)(q.bt.n + b) * q.P;
+  const int* ids_cur = q.ids + (long long)fr * q.P;
   const int* ids_pre = q.ids + (long long)(fr > 0 ? fr - 1 : 0) * q.P;
+  const float4* own1 = q.own1 + (long long)b * q.h1 * q.w1;
   float acc_flow = 0.f, acc_tvh = 0.f, acc_tvw = 0.f;
 
   auto sink = [&](int id, unsigned fl, float g0, float g1, float g2) {
-    if (!(fl & 7)) return;
     int owner, local;
     shard_of<W1>(sh, id, owner, local);
     red_add_v4(sh.grad[owner] + (long long)local * 4, (fl & 1) ? g0 * SH_C0 : 0.f, (fl & 2) ? g1 * SH_C0 : 0.f,
                (fl & 4) ? g2 * SH_C0 : 0.f);
   };
+  // gradient a[] of the predecessor pixel (xx, yy) whose clamp flags are fl (0 outside the image)
+  auto flush = [&](const float (&a)[3], int xx, int yy, unsigned fl) {
+    if (!fl) return;
+    if (a[0] == 0.f && a[1] == 0.f && a[2] == 0.f) return;
+    sink(ids_pre[yy * q.W + xx], fl, a[0], a[1], a[2]);
+  };
 
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long pw = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); pw < q.P; pw += stride) {   // warp-uniform trip count
-    const long long p = pw + lane;
-    const bool act = p < q.P;
-    const int x = act ? (int)(p % q.W) : 0, y = act ? (int)(p / q.W) : 0;
-    float xi[3] = {0.f, 0.f, 0.f}, g[3] = {0.f, 0.f, 0.f};
-    if (act) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) xi[c] = Xi[c * q.P + p];
-    }
+  const int n_seg = (q.W + SEG - 1) / SEG;
+  const int n_chunks = q.H * n_seg;
+  for (int ch = blockIdx.x * 8 + warp; ch < n_chunks; ch += gridDim.x * 8) {       // warp-uniform
+    const int y = ch / n_seg, seg = ch - y * n_seg;
+    const int x = seg * SEG - 3 + lane;
+    const bool act = x >= 0 && x < q.W;
+    const bool real = act && lane >= 3;
+    const bool next_exists = (seg + 1) * SEG < q.W;
+    const int p = y * q.W + x;
+    float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) own = Xi[p];
+    float g[3] = {0.f, 0.f, 0.f};
     // ---- flow term: warp the predecessor with the backward flow ----
     if (valid) {
       Bicubic bc;
@@ -578,78 +637,113 @@ level0_uvt_kernel(L0Params q, Shards sh) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) bc.cx[i] = bc.cy[i] = 0.f;
       float s[3] = {0.f, 0.f, 0.f};
+      unsigned tf[2] = {0u, 0u};
       if (act) {
         bicubic_setup(q, fr, p, x, y, bc);
         float wv[3];
-        bicubic_sample(q, Xp, bc, wv);
+        bicubic_sample(q, Xp, bc, wv, tf);
         const float m = q.mask[(long long)fr * q.P + p];
+        const float xi[3] = {own.x, own.y, own.z};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float d = wv[c] * m - xi[c] * m;
-          acc_flow += fabsf(d);
           const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
           s[c] = sg * m * q.k_flow;
-          g[c] -= s[c];
+          if (real) { acc_flow += fabsf(d); g[c] -= s[c]; }
         }
       }
-      // links of the systolic row sums: lane l continues the chain of lane l-1 iff their footprints are one column apart
+      // chain links: lane l continues lane l-1 iff their footprints are one column apart on the same rows
       const int x0l = __shfl_up_sync(FULL, bc.x0, 1), y0l = __shfl_up_sync(FULL, bc.y0, 1);
       const bool link = lane > 0 && bc.x0 == x0l + 1 && bc.y0 == y0l;
-      const int link_next = __shfl_down_sync(FULL, (int)link, 1);     // every lane shuffles (no short-circuit around a .sync)
-      const bool link_r = lane < 31 && link_next;
-      auto flush = [&](float a0, float a1, float a2, int xx, int yy) {
-        if (xx < 0 || xx >= q.W || yy < 0 || yy >= q.H) return;
-        if (a0 == 0.f && a1 == 0.f && a2 == 0.f) return;
-        const long long o = (long long)yy * q.W + xx;
-        sink(ids_pre[o], fl_pre[o], a0, a1, a2);
-      };
+      const unsigned lb = __ballot_sync(FULL, link);
+      // lane m accepts the tap-k value of lane m-k iff links m-k+1..m are intact (helpers own no column here)
+      bool acc[4];
+      unsigned ab[4];
+#pragma unroll
+      for (int k = 1; k <= 3; ++k) {
+        const unsigned need = ((1u << k) - 1u) << ((lane - k + 1) & 31);
+        acc[k] = real && lane >= k && (lb & need) == need;
+        ab[k] = __ballot_sync(FULL, acc[k]);
+      }
+      // tap i of this lane is left over (reduced by the producer) iff nobody accepts it; a real lane defers taps whose
+      // consumer would sit in the next segment, a helper handles exactly the taps its pixel deferred there
+      bool left[4];
+#pragma unroll
+      for (int i = 1; i <= 3; ++i) {
+        const bool cons = lane + i <= 31 && ((ab[i] >> ((lane + i) & 31)) & 1u);
+        left[i] = act && !cons && (lane >= 3 ? (lane + i <= 31 || !next_exists) : (lane + i >= 3));
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int yy = bc.y0 + j;
         const float wy = bc.cy[j];
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        float v[4][3];
 #pragma unroll
-        for (int st = 0; st < 4; ++st) {
-          const float wgt = bc.cx[3 - st] * wy;
-          if (st > 0) {
-            const float r0 = __shfl_up_sync(FULL, a0, 1), r1 = __shfl_up_sync(FULL, a1, 1), r2 = __shfl_up_sync(FULL, a2, 1);
-            a0 = link ? r0 : 0.f; a1 = link ? r1 : 0.f; a2 = link ? r2 : 0.f;
-          }
-          a0 += s[0] * wgt; a1 += s[1] * wgt; a2 += s[2] * wgt;
-          if (st == 3 || !link_r) flush(a0, a1, a2, bc.x0 + 3 - st, yy);
+        for (int i = 0; i < 4; ++i) {
+          const float wgt = bc.cx[i] * wy;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v[i][c] = s[c] * wgt;
         }
+        float out[3] = {v[0][0], v[0][1], v[0][2]};
+#pragma unroll
+        for (int k = 1; k <= 3; ++k)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float r = __shfl_up_sync(FULL, v[k][c], k);
+            out[c] += acc[k] ? r : 0.f;
+          }
+        if (real) flush(out, bc.x0, yy, tap_flags(tf, j, 0));
+#pragma unroll
+        for (int i = 1; i <= 3; ++i)
+          if (left[i]) flush(v[i], bc.x0 + i, yy, tap_flags(tf, j, i));
       }
     }
-    if (!act) continue;
+    if (!real) continue;
     // ---- total variation ----
     if (q.k_tvh != 0.f) {
+      const float xi[3] = {own.x, own.y, own.z};
+      float gg[3] = {0.f, 0.f, 0.f};
+      if (y + 1 < q.H) {
+        const float4 t = __ldg(Xi + p + q.W);
+        const float d[3] = {t.x - xi[0], t.y - xi[1], t.z - xi[2]};
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float* pl = Xi + c * q.P;
-        const float v = xi[c];
-        float gg = 0.f;
-        if (y + 1 < q.H) { const float d = pl[p + q.W] - v; acc_tvh += d * d; gg -= q.k_tvh * 2.f * d; }
-        if (y > 0) gg += q.k_tvh * 2.f * (v - pl[p - q.W]);
-        if (x + 1 < q.W) { const float d = pl[p + 1] - v; acc_tvw += d * d; gg -= q.k_tvw * 2.f * d; }
-        if (x > 0) gg += q.k_tvw * 2.f * (v - pl[p - 1]);
-        g[c] += gg;
+        for (int c = 0; c < 3; ++c) { acc_tvh += d[c] * d[c]; gg[c] -= q.k_tvh * 2.f * d[c]; }
+      }
+      if (y > 0) {
+        const float4 t = __ldg(Xi + p - q.W);
+        gg[0] += q.k_tvh * 2.f * (xi[0] - t.x); gg[1] += q.k_tvh * 2.f * (xi[1] - t.y); gg[2] += q.k_tvh * 2.f * (xi[2] - t.z);
+      }
+      if (x + 1 < q.W) {
+        const float4 t = __ldg(Xi + p + 1);
+        const float d[3] = {t.x - xi[0], t.y - xi[1], t.z - xi[2]};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { acc_tvw += d[c] * d[c]; gg[c] -= q.k_tvw * 2.f * d[c]; }
+      }
+      if (x > 0) {
+        const float4 t = __ldg(Xi + p - 1);
+        gg[0] += q.k_tvw * 2.f * (xi[0] - t.x); gg[1] += q.k_tvw * 2.f * (xi[1] - t.y); gg[2] += q.k_tvw * 2.f * (xi[2] - t.z);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) g[c] += gg[c];
+    }
+    // ---- MS-SSIM gradient (collapsed chain at level-1 resolution) ----
+    {
+      const int y1 = (y + q.ph0) >> 1, x1 = (x + q.pw0) >> 1;
+      if (y1 < q.h1 && x1 < q.w1) {
+        const float4 t = __ldg(own1 + y1 * q.w1 + x1);
+        g[0] += t.x; g[1] += t.y; g[2] += t.z;
       }
     }
-    // ---- MS-SSIM gradient chain ----
-#pragma unroll
-    for (int c = 0; c < 3; ++c) g[c] += msssim_grad(q.own + (long long)(b * 3 + c) * q.own_stride, q.py, y, x);
     // ---- sink ----
-    sink(q.ids[(long long)fr * q.P + p], q.flags[(long long)b * q.P + p], g[0], g[1], g[2]);
+    const unsigned fl = __float_as_uint(own.w) & 7u;
+    if (fl) sink(ids_cur[p], fl, g[0], g[1], g[2]);
   }
   acc_flow = warp_sum(acc_flow); acc_tvh = warp_sum(acc_tvh); acc_tvw = warp_sum(acc_tvw);
-  if (lane == 0) {
-    const int wq = threadIdx.x >> 5;
-    red[0][wq] = acc_flow; red[1][wq] = acc_tvh; red[2][wq] = acc_tvw;
-  }
+  if (lane == 0) { red[0][warp] = acc_flow; red[1][warp] = acc_tvh; red[2][warp] = acc_tvw; }
   __syncthreads();
   if (threadIdx.x == 0) {
     float a = 0.f, bb = 0.f, cc = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; bb += red[1][i]; cc += red[2][i]; }
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; bb += red[1][i]; cc += red[2][i]; }
     atomicAdd(&q.scal[SC_FLOW_ABS], a); atomicAdd(&q.scal[SC_TV_H], bb); atomicAdd(&q.scal[SC_TV_W], cc);
   }
 }
@@ -665,23 +759,25 @@ level0_expo_kernel(L0Params q) {
   const int b = blockIdx.y;
   const int fr = q.bt.idx[b];
   const bool valid = fr > 0;
-  const float* Xi = q.X + (long long)b * 3 * q.P;
-  const float* Xp = q.X + (long long)(q.bt.n + b) * 3 * q.P;
+  const float4* Xi = q.X + (long long)b * q.P;
+  const float4* Xp = q.X + (long long)(q.bt.n + b) * q.P;
+  const float4* own1 = q.own1 + (long long)b * q.h1 * q.w1;
   float acc_flow = 0.f, acc_l1 = 0.f;
   float ge[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) ge[k] = 0.f;
   if (threadIdx.x < 12) eg[threadIdx.x] = 0.f;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < q.P; p += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(p % q.W), y = (int)(p / q.W);
-    float xi[3], g[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { xi[c] = Xi[c * q.P + p]; g[c] = 0.f; }
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < q.P; p += gridDim.x * blockDim.x) {
+    const int y = p / q.W, x = p - y * q.W;
+    const float4 own = Xi[p];
+    const float xi[3] = {own.x, own.y, own.z};
+    float g[3] = {0.f, 0.f, 0.f};
     if (valid) {
       Bicubic bc;
       bicubic_setup(q, fr, p, x, y, bc);
       float wv[3];
-      bicubic_sample(q, Xp, bc, wv);
+      unsigned tf[2];
+      bicubic_sample(q, Xp, bc, wv, tf);
       const float m = q.mask[(long long)fr * q.P + p];
       float s[3];
 #pragma unroll
@@ -717,9 +813,14 @@ level0_expo_kernel(L0Params q) {
       acc_l1 += fabsf(d);
       g[c] += q.k_l1 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
     }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) g[c] += msssim_grad(q.own + (long long)(b * 3 + c) * q.own_stride, q.py, y, x);
-    const unsigned char fl = q.flags[(long long)b * q.P + p];
+    {
+      const int y1 = (y + q.ph0) >> 1, x1 = (x + q.pw0) >> 1;
+      if (y1 < q.h1 && x1 < q.w1) {
+        const float4 t = __ldg(own1 + y1 * q.w1 + x1);
+        g[0] += t.x; g[1] += t.y; g[2] += t.z;
+      }
+    }
+    const unsigned fl = __float_as_uint(own.w);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const float gj = ((fl >> j) & 1) ? g[j] : 0.f;
@@ -755,12 +856,13 @@ pre_sink_kernel(L0Params q) {
   for (int k = 0; k < 12; ++k) ge[k] = 0.f;
   if (threadIdx.x < 12) eg[threadIdx.x] = 0.f;
   float4* Gp = reinterpret_cast<float4*>(q.G_pre + (long long)b * 4 * q.P);
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < q.P; p += (long long)gridDim.x * blockDim.x) {
+  const float4* Xpre = q.X + (long long)(q.bt.n + b) * q.P;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < q.P; p += gridDim.x * blockDim.x) {
     const float4 gv = Gp[p];
     if (gv.x == 0.f && gv.y == 0.f && gv.z == 0.f) continue;
     Gp[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float g[3] = {gv.x, gv.y, gv.z};
-    const unsigned char fl = q.flags[(long long)(q.bt.n + b) * q.P + p];
+    const unsigned fl = __float_as_uint(Xpre[p].w);
     float in[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) in[c] = q.edited[((long long)fr * 3 + c) * q.P + p];
@@ -943,7 +1045,7 @@ static int ensure_gauss() {
 
 // workspace carving ---------------------------------------------------------------------
 struct Ws {
-  float* X; unsigned char* flags; float* G_pre; float* xpyr; float* pm; float* own; float* sums; float* coef; float* scal;
+  float4* X; float* G_pre; float* xpyr; float* pm; float* own; float4* own1; float* sums; float* coef; float* scal;
 };
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t ws_layout(void* base, int H, int W, int nb, Ws* w) {
@@ -952,12 +1054,12 @@ static size_t ws_layout(void* base, int H, int W, int nb, Ws* w) {
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   auto take = [&](size_t bytes) { uint8_t* r = p; p += align_up(bytes); return r; };
   Ws t;
-  t.X = (float*)take(sizeof(float) * 2 * nb * 3 * P);
-  t.flags = take((size_t)2 * nb * P);
+  t.X = (float4*)take(sizeof(float4) * 2 * nb * P);              // {R,G,B,flags} per pixel, batch frames then predecessors
   t.G_pre = (float*)take(sizeof(float) * nb * 4 * P);             // stage 1 only: [nb,P,4], zero between iterations
   t.xpyr = (float*)take(sizeof(float) * nb * 3 * py.total);       // X pyramid levels 1..4
   t.pm = (float*)take(sizeof(float) * nb * 3 * 3 * py.total);     // d(map)/d(mu1, e11, e12) per level
   t.own = (float*)take(sizeof(float) * nb * 3 * py.total);        // per-level MS-SSIM gradient
+  t.own1 = (float4*)take(sizeof(float4) * nb * (size_t)py.h[1] * py.w[1]);   // its pooled-down chain at level-1 resolution
   t.sums = (float*)take(sizeof(float) * (4 * nb * 3 * 2 + SC_COUNT));   // level sums, then the scalars (one memset)
   t.scal = t.sums + 4 * nb * 3 * 2;
   t.coef = (float*)take(sizeof(float) * 4 * nb * 3);
@@ -1036,6 +1138,7 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
   const long long P = (long long)H * W;
   Pyr py; make_pyr(H, W, &py);
   TCL_CHECK_ARG(py.h[4] >= 11 && py.w[4] >= 11, "postopt: image too small for 5-level MS-SSIM");
+  TCL_CHECK_ARG(P < (1ll << 30), "postopt: frames of %lld pixels are not supported (32-bit pixel offsets)", P);
   Ws w; ws_layout(c->workspace, H, W, c->max_batch, &w);   // fixed layout: G_pre must stay zero between iterations
   Batch bt; bt.n = nb;
   int n_valid = 0;
@@ -1060,23 +1163,26 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
   if (stage == 2) {
     if (H % 2 == 0 && W % 2 == 0) {
       const long long quads = (long long)2 * nb * (P / 4);
-      if (w1) uvt_gather_quad_kernel<true><<<gridp(quads, 256, 148 * 16), 256, 0, stream>>>(sh, ids, H, W, bt, w.X, w.flags, w.xpyr + py.off[1], py.total);
-      else uvt_gather_quad_kernel<false><<<gridp(quads, 256, 148 * 16), 256, 0, stream>>>(sh, ids, H, W, bt, w.X, w.flags, w.xpyr + py.off[1], py.total);
+      if (w1) uvt_gather_quad_kernel<true><<<gridp(quads, 256, 148 * 16), 256, 0, stream>>>(sh, ids, H, W, bt, w.X, w.xpyr + py.off[1], py.total);
+      else uvt_gather_quad_kernel<false><<<gridp(quads, 256, 148 * 16), 256, 0, stream>>>(sh, ids, H, W, bt, w.X, w.xpyr + py.off[1], py.total);
       first_pool = 1;
     } else {
-      if (w1) uvt_gather_kernel<true><<<gridp(2 * nb * P, 256, 148 * 16), 256, 0, stream>>>(sh, ids, P, bt, w.X, w.flags);
-      else uvt_gather_kernel<false><<<gridp(2 * nb * P, 256, 148 * 16), 256, 0, stream>>>(sh, ids, P, bt, w.X, w.flags);
+      if (w1) uvt_gather_kernel<true><<<gridp(2 * nb * P, 256, 148 * 16), 256, 0, stream>>>(sh, ids, P, bt, w.X);
+      else uvt_gather_kernel<false><<<gridp(2 * nb * P, 256, 148 * 16), 256, 0, stream>>>(sh, ids, P, bt, w.X);
     }
   } else {
-    exposure_apply_kernel<<<gridp(2 * nb * P, 256, 148 * 16), 256, 0, stream>>>(c->edited, expo, P, bt, w.X, w.flags);
+    exposure_apply_kernel<<<gridp(2 * nb * P, 256, 148 * 16), 256, 0, stream>>>(c->edited, expo, P, bt, w.X);
   }
   TCL_CHECK_LAUNCH("postopt(produce)");
   // 2. pyramid of the batch frames
-  for (int l = first_pool; l < 4; ++l) {
-    const float* in = l == 0 ? w.X : w.xpyr + py.off[l];
-    const long long in_stride = l == 0 ? P : py.total;
+  if (first_pool == 0) {
+    avgpool2_x4_kernel<<<gridp((long long)nb * py.h[1] * py.w[1], 256), 256, 0, stream>>>(w.X, P, H, W, py.ph[0], py.pw[0],
+                                                                                        w.xpyr + py.off[1], py.total, py.h[1], py.w[1], nb);
+    TCL_CHECK_LAUNCH("postopt(pyramid)");
+  }
+  for (int l = 1; l < 4; ++l) {
     const long long total = (long long)planes * py.h[l + 1] * py.w[l + 1];
-    avgpool2_kernel<<<gridp(total, 256), 256, 0, stream>>>(in, in_stride, py.h[l], py.w[l], py.ph[l], py.pw[l],
+    avgpool2_kernel<<<gridp(total, 256), 256, 0, stream>>>(w.xpyr + py.off[l], py.total, py.h[l], py.w[l], py.ph[l], py.pw[l],
                                                            w.xpyr + py.off[l + 1], py.total, py.h[l + 1], py.w[l + 1], planes);
     TCL_CHECK_LAUNCH("postopt(pyramid)");
   }
@@ -1097,11 +1203,13 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
   ssim_bwd_all_kernel<<<lpb.first[5], 256, 0, stream>>>(w.xpyr, py.total, c->ypyr, 3 * py.total, py.total, bt, lpb, w.coef, w.pm,
                                                         py.total, w.own, py.total);
   TCL_CHECK_LAUNCH("postopt(ssim_bwd)");
+  own_collapse_kernel<<<gridp((long long)nb * py.h[1] * py.w[1], 256), 256, 0, stream>>>(w.own, py.total, py, nb, w.own1);
+  TCL_CHECK_LAUNCH("postopt(collapse)");
   // 6. fused level-0 kernel (+ stage 1: predecessor sink)
   L0Params q;
   memset(&q, 0, sizeof(q));
-  q.H = H; q.W = W; q.P = P; q.bt = bt; q.X = w.X; q.flags = w.flags; q.flows = c->past_flows; q.mask = c->mask_bwd;
-  q.own = w.own; q.own_stride = py.total; q.py = py;
+  q.H = H; q.W = W; q.P = (int)P; q.bt = bt; q.X = w.X; q.flows = c->past_flows; q.mask = c->mask_bwd;
+  q.own1 = w.own1; q.h1 = py.h[1]; q.w1 = py.w[1]; q.ph0 = py.ph[0]; q.pw0 = py.pw[0];
   const int n_valid_g = c->norm_batch > 0 ? c->norm_valid : n_valid;
   const float flow_cnt = (float)n_valid_g * 3.f * (float)P;
   q.k_flow = n_valid_g > 0 ? c->lambda_flow / flow_cnt : 0.f;
@@ -1111,7 +1219,9 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
   q.edited = c->edited; q.G_pre = w.G_pre; q.scal = w.scal; q.ids = ids; q.grad_expo = egrad;
   dim3 g0(gridp(P, 256, 148 * 2), nb);
   if (stage == 2) {
-    if (w1) level0_uvt_kernel<true><<<g0, 256, 0, stream>>>(q, sh); else level0_uvt_kernel<false><<<g0, 256, 0, stream>>>(q, sh);
+    const long long chunks = (long long)H * ((W + SEG - 1) / SEG);
+    dim3 gu(gridp(chunks * 32, 256, 148 * 2), nb);
+    if (w1) level0_uvt_kernel<true><<<gu, 256, 0, stream>>>(q, sh); else level0_uvt_kernel<false><<<gu, 256, 0, stream>>>(q, sh);
     TCL_CHECK_LAUNCH("postopt(level0)");
   } else {
     level0_expo_kernel<<<g0, 256, 0, stream>>>(q);
