@@ -550,13 +550,29 @@ __device__ __forceinline__ void bicubic_setup(const L0Params& q, int fr, int p, 
   cubic_coeffs(iy - fy0, bc.cy);
   bc.x0 = (int)fx0 - 1; bc.y0 = (int)fy0 - 1;
 }
-// 16 taps of 16 bytes; tf[j>>1] collects the taps' clamp flags, 3 bits per tap at bit 3*(4*(j&1)+i) (0 for taps outside
-// the image: they carry no gradient either)
+// 16 taps of 16 bytes; tf collects the clamp flags of the four column-0 taps, 3 bits per row at bit 3*j (0 for taps
+// outside the image: they carry no gradient either)
 __device__ __forceinline__ void bicubic_sample(const L0Params& q, const float4* __restrict__ Xp, const Bicubic& bc, float (&wv)[3],
-                                               unsigned (&tf)[2]) {
+                                               unsigned& tf) {
   wv[0] = wv[1] = wv[2] = 0.f;
-  tf[0] = tf[1] = 0u;
-  const bool inx = bc.x0 >= 0 && bc.x0 + 3 < q.W;
+  tf = 0u;
+  if (bc.x0 >= 0 && bc.x0 + 3 < q.W && bc.y0 >= 0 && bc.y0 + 3 < q.H) {       // interior: no per-tap tests
+    const float4* rowp = Xp + (bc.y0 * q.W + bc.x0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 t0 = __ldg(rowp), t1 = __ldg(rowp + 1), t2 = __ldg(rowp + 2), t3 = __ldg(rowp + 3);
+      rowp += q.W;
+      float row[3];
+      row[0] = t0.x * bc.cx[0]; row[1] = t0.y * bc.cx[0]; row[2] = t0.z * bc.cx[0];
+      row[0] += t1.x * bc.cx[1]; row[1] += t1.y * bc.cx[1]; row[2] += t1.z * bc.cx[1];
+      row[0] += t2.x * bc.cx[2]; row[1] += t2.y * bc.cx[2]; row[2] += t2.z * bc.cx[2];
+      row[0] += t3.x * bc.cx[3]; row[1] += t3.y * bc.cx[3]; row[2] += t3.z * bc.cx[3];
+      tf |= (__float_as_uint(t0.w) & 7u) << (3 * j);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) wv[c] += row[c] * bc.cy[j];
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int yy = bc.y0 + j;
@@ -565,16 +581,15 @@ __device__ __forceinline__ void bicubic_sample(const L0Params& q, const float4* 
     float row[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if (!inx && (bc.x0 + i < 0 || bc.x0 + i >= q.W)) continue;
+      if (bc.x0 + i < 0 || bc.x0 + i >= q.W) continue;
       const float4 t = __ldg(rowp + i);
       row[0] += t.x * bc.cx[i]; row[1] += t.y * bc.cx[i]; row[2] += t.z * bc.cx[i];
-      tf[j >> 1] |= (__float_as_uint(t.w) & 7u) << (3 * (4 * (j & 1) + i));
+      if (i == 0) tf |= (__float_as_uint(t.w) & 7u) << (3 * j);
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) wv[c] += row[c] * bc.cy[j];
   }
 }
-__device__ __forceinline__ unsigned tap_flags(const unsigned (&tf)[2], int j, int i) { return (tf[j >> 1] >> (3 * (4 * (j & 1) + i))) & 7u; }
 
 // ------------------------------------------------------------------------------------------
 // Stage 2, fused level-0 kernel: bicubic flow warp forward + backward, masked L1, TV, MS-SSIM gradient, and the gradient
@@ -590,8 +605,8 @@ __device__ __forceinline__ unsigned tap_flags(const unsigned (&tf)[2], int j, in
 // ------------------------------------------------------------------------------------------
 constexpr int SEG = 29;
 template <bool W1>
-__global__ void __launch_bounds__(256)
-level0_uvt_kernel(L0Params q, Shards sh) {
+__global__ void __launch_bounds__(256, 4)
+level0_uvt_kernel(L0Params q, Shards sh, float inv_nseg) {
   __shared__ float red[3][8];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -611,17 +626,13 @@ level0_uvt_kernel(L0Params q, Shards sh) {
     red_add_v4(sh.grad[owner] + (long long)local * 4, (fl & 1) ? g0 * SH_C0 : 0.f, (fl & 2) ? g1 * SH_C0 : 0.f,
                (fl & 4) ? g2 * SH_C0 : 0.f);
   };
-  // gradient a[] of the predecessor pixel (xx, yy) whose clamp flags are fl (0 outside the image)
-  auto flush = [&](const float (&a)[3], int xx, int yy, unsigned fl) {
-    if (!fl) return;
-    if (a[0] == 0.f && a[1] == 0.f && a[2] == 0.f) return;
-    sink(ids_pre[yy * q.W + xx], fl, a[0], a[1], a[2]);
-  };
 
   const int n_seg = (q.W + SEG - 1) / SEG;
   const int n_chunks = q.H * n_seg;
   for (int ch = blockIdx.x * 8 + warp; ch < n_chunks; ch += gridDim.x * 8) {       // warp-uniform
-    const int y = ch / n_seg, seg = ch - y * n_seg;
+    int y = __float2int_rz(((float)ch + 0.5f) * inv_nseg);
+    if (y * n_seg > ch) --y; else if ((y + 1) * n_seg <= ch) ++y;
+    const int seg = ch - y * n_seg;
     const int x = seg * SEG - 3 + lane;
     const bool act = x >= 0 && x < q.W;
     const bool real = act && lane >= 3;
@@ -637,7 +648,7 @@ level0_uvt_kernel(L0Params q, Shards sh) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) bc.cx[i] = bc.cy[i] = 0.f;
       float s[3] = {0.f, 0.f, 0.f};
-      unsigned tf[2] = {0u, 0u};
+      unsigned tf = 0u;
       if (act) {
         bicubic_setup(q, fr, p, x, y, bc);
         float wv[3];
@@ -657,26 +668,32 @@ level0_uvt_kernel(L0Params q, Shards sh) {
       const bool link = lane > 0 && bc.x0 == x0l + 1 && bc.y0 == y0l;
       const unsigned lb = __ballot_sync(FULL, link);
       // lane m accepts the tap-k value of lane m-k iff links m-k+1..m are intact (helpers own no column here)
-      bool acc[4];
+      float accf[4];
       unsigned ab[4];
 #pragma unroll
       for (int k = 1; k <= 3; ++k) {
         const unsigned need = ((1u << k) - 1u) << ((lane - k + 1) & 31);
-        acc[k] = real && lane >= k && (lb & need) == need;
-        ab[k] = __ballot_sync(FULL, acc[k]);
+        const bool a = real && lane >= k && (lb & need) == need;
+        accf[k] = a ? 1.f : 0.f;
+        ab[k] = __ballot_sync(FULL, a);
       }
       // tap i of this lane is left over (reduced by the producer) iff nobody accepts it; a real lane defers taps whose
       // consumer would sit in the next segment, a helper handles exactly the taps its pixel deferred there
-      bool left[4];
+      unsigned left = 0u;
 #pragma unroll
       for (int i = 1; i <= 3; ++i) {
         const bool cons = lane + i <= 31 && ((ab[i] >> ((lane + i) & 31)) & 1u);
-        left[i] = act && !cons && (lane >= 3 ? (lane + i <= 31 || !next_exists) : (lane + i >= 3));
+        if (act && !cons && (lane >= 3 ? (lane + i <= 31 || !next_exists) : (lane + i >= 3))) left |= 1u << i;
       }
+      if (s[0] == 0.f && s[1] == 0.f && s[2] == 0.f) left = 0u;
+      const bool main_on = real && tf != 0u;
+      const int o0 = bc.y0 * q.W + bc.x0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int yy = bc.y0 + j;
         const float wy = bc.cy[j];
+        const unsigned fl = (tf >> (3 * j)) & 7u;
+        int id = 0;
+        if (main_on && fl) id = __ldg(ids_pre + o0 + j * q.W);
         float v[4][3];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -688,14 +705,20 @@ level0_uvt_kernel(L0Params q, Shards sh) {
 #pragma unroll
         for (int k = 1; k <= 3; ++k)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float r = __shfl_up_sync(FULL, v[k][c], k);
-            out[c] += acc[k] ? r : 0.f;
-          }
-        if (real) flush(out, bc.x0, yy, tap_flags(tf, j, 0));
+          for (int c = 0; c < 3; ++c) out[c] = fmaf(__shfl_up_sync(FULL, v[k][c], k), accf[k], out[c]);
+        if (main_on && fl) sink(id, fl, out[0], out[1], out[2]);
+        if (left) {                                  // rare: broken chain / image border
+          const int yy = bc.y0 + j;
+          if (yy >= 0 && yy < q.H) {
 #pragma unroll
-        for (int i = 1; i <= 3; ++i)
-          if (left[i]) flush(v[i], bc.x0 + i, yy, tap_flags(tf, j, i));
+            for (int i = 1; i <= 3; ++i) {
+              const int xx = bc.x0 + i;
+              if (!((left >> i) & 1u) || xx < 0 || xx >= q.W) continue;
+              const unsigned fli = __float_as_uint(__ldg(Xp + yy * q.W + xx).w) & 7u;
+              if (fli) sink(ids_pre[yy * q.W + xx], fli, v[i][0], v[i][1], v[i][2]);
+            }
+          }
+        }
       }
     }
     if (!real) continue;
@@ -776,7 +799,7 @@ level0_expo_kernel(L0Params q) {
       Bicubic bc;
       bicubic_setup(q, fr, p, x, y, bc);
       float wv[3];
-      unsigned tf[2];
+      unsigned tf;
       bicubic_sample(q, Xp, bc, wv, tf);
       const float m = q.mask[(long long)fr * q.P + p];
       float s[3];
@@ -922,46 +945,36 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   }
 }
 
-// Stage-2 Adam over the UVT rows: p, m, v are [U,3], the gradient is [U,4] (lane 3 padding).  One thread handles four
-// rows = three float4 of p/m/v and four float4 of g, so every access is a 16-byte vector.
+// Stage-2 Adam over the UVT rows: p, m, v are [U,3], the gradient is [U,4] (lane 3 padding, never read or written here:
+// the reductions only ever add 0 to it).  One thread handles one float4 of the flat p/m/v arrays, so the three big streams
+// are perfectly coalesced 16-byte accesses; its four gradient values (rows 4a + {0,0,0,1 | 1,1,2,2 | 2,3,3,3}) are scalar
+// loads from a span the warp shares.
 __global__ void __launch_bounds__(256)
 adam_uvt_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long U,
                 float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt) {
   const float step_size = lr / bc1;
-  const long long quads = U / 4;
+  const long long quads = U / 4;           // groups of 4 rows = 3 float4 of p/m/v = 16 floats of g
+  const long long n4 = quads * 3;
   auto upd = [&](float& pi, float gi, float& mi, float& vi) {
     mi = mi + (gi - mi) * (1.f - beta1);
     vi = vi * beta2 + (1.f - beta2) * gi * gi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     pi = pi - step_size * (mi / denom);
   };
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < quads; t += (long long)gridDim.x * blockDim.x) {
-    float4* p4 = reinterpret_cast<float4*>(p) + t * 3;
-    float4* m4 = reinterpret_cast<float4*>(m) + t * 3;
-    float4* v4 = reinterpret_cast<float4*>(v) + t * 3;
-    float4* g4 = reinterpret_cast<float4*>(g) + t * 4;
-    float pa[12], ma[12], va[12], ga[12];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float4 a = p4[k], b = m4[k], c = v4[k];
-      pa[4 * k] = a.x; pa[4 * k + 1] = a.y; pa[4 * k + 2] = a.z; pa[4 * k + 3] = a.w;
-      ma[4 * k] = b.x; ma[4 * k + 1] = b.y; ma[4 * k + 2] = b.z; ma[4 * k + 3] = b.w;
-      va[4 * k] = c.x; va[4 * k + 1] = c.y; va[4 * k + 2] = c.z; va[4 * k + 3] = c.w;
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float4 a = g4[r];
-      ga[3 * r] = a.x; ga[3 * r + 1] = a.y; ga[3 * r + 2] = a.z;
-      g4[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int k = 0; k < 12; ++k) upd(pa[k], ga[k], ma[k], va[k]);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      p4[k] = make_float4(pa[4 * k], pa[4 * k + 1], pa[4 * k + 2], pa[4 * k + 3]);
-      m4[k] = make_float4(ma[4 * k], ma[4 * k + 1], ma[4 * k + 2], ma[4 * k + 3]);
-      v4[k] = make_float4(va[4 * k], va[4 * k + 1], va[4 * k + 2], va[4 * k + 3]);
-    }
+  for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < n4; f += (long long)gridDim.x * blockDim.x) {
+    const long long a = f / 3;
+    const int b = (int)(f - a * 3);
+    // gradient offsets inside the 16-float group: element e = 4b + k -> row e / 3, channel e % 3 -> 4 * row + channel
+    const int o0 = b == 0 ? 0 : (b == 1 ? 5 : 10);
+    const int o1 = b == 0 ? 1 : (b == 1 ? 6 : 12);
+    const int o2 = b == 0 ? 2 : (b == 1 ? 8 : 13);
+    const int o3 = b == 0 ? 4 : (b == 1 ? 9 : 14);
+    float* gg = g + a * 16;
+    const float g0 = gg[o0], g1 = gg[o1], g2 = gg[o2], g3 = gg[o3];
+    float4 pa = reinterpret_cast<float4*>(p)[f], ma = reinterpret_cast<float4*>(m)[f], va = reinterpret_cast<float4*>(v)[f];
+    upd(pa.x, g0, ma.x, va.x); upd(pa.y, g1, ma.y, va.y); upd(pa.z, g2, ma.z, va.z); upd(pa.w, g3, ma.w, va.w);
+    reinterpret_cast<float4*>(p)[f] = pa; reinterpret_cast<float4*>(m)[f] = ma; reinterpret_cast<float4*>(v)[f] = va;
+    gg[o0] = 0.f; gg[o1] = 0.f; gg[o2] = 0.f; gg[o3] = 0.f;
   }
   // tail rows (U % 4)
   if (blockIdx.x == 0 && threadIdx.x < 3 * (int)(U - quads * 4)) {
@@ -1221,7 +1234,9 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
   if (stage == 2) {
     const long long chunks = (long long)H * ((W + SEG - 1) / SEG);
     dim3 gu(gridp(chunks * 32, 256, 148 * 2), nb);
-    if (w1) level0_uvt_kernel<true><<<gu, 256, 0, stream>>>(q, sh); else level0_uvt_kernel<false><<<gu, 256, 0, stream>>>(q, sh);
+    const float inv_nseg = 1.f / (float)((W + SEG - 1) / SEG);
+    if (w1) level0_uvt_kernel<true><<<gu, 256, 0, stream>>>(q, sh, inv_nseg);
+    else level0_uvt_kernel<false><<<gu, 256, 0, stream>>>(q, sh, inv_nseg);
     TCL_CHECK_LAUNCH("postopt(level0)");
   } else {
     level0_expo_kernel<<<g0, 256, 0, stream>>>(q);
@@ -1244,7 +1259,7 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
     TCL_CHECK_LAUNCH("postopt(loss)");
     if (do_adam) {
       const long long rows = shards->rows_per_rank;
-      adam_uvt_kernel<<<gridp(rows / 4 + 1, 256, 148 * 16), 256, 0, stream>>>(shards->fdc[shards->rank], shards->grad[shards->rank], m, v,
+      adam_uvt_kernel<<<gridp(rows / 4 * 3 + 1, 256, 148 * 16), 256, 0, stream>>>(shards->fdc[shards->rank], shards->grad[shards->rank], m, v,
                                                                              rows, lr, beta1, beta2, eps, bc1, bc2_sqrt);
       TCL_CHECK_LAUNCH("postopt(adam)");
     }
@@ -1341,7 +1356,7 @@ extern "C" int tcl_adam_step_uvt(float* fdc, float* grad4, float* m, float* v, l
   TCL_CHECK_ARG(fdc && grad4 && m && v && U > 0 && step >= 1, "tcl_adam_step_uvt: args");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
-  adam_uvt_kernel<<<gridp(U / 4 + 1, 256, 148 * 16), 256, 0, stream>>>(fdc, grad4, m, v, U, lr, beta1, beta2, eps, bc1, bc2_sqrt);
+  adam_uvt_kernel<<<gridp(U / 4 * 3 + 1, 256, 148 * 16), 256, 0, stream>>>(fdc, grad4, m, v, U, lr, beta1, beta2, eps, bc1, bc2_sqrt);
   TCL_CHECK_LAUNCH("tcl_adam_step_uvt");
   return TCL_OK;
 }
