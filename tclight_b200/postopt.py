@@ -114,10 +114,14 @@ def _shard_info(gen):
 
 
 def shard_batch(idxs, rank: int, world: int):
-    """This rank's slice of a batch (round robin) plus the global normalisers: every rank draws the same
-    batches (same CPU RNG state, see _sync_cpu_rng), processes idxs[rank::world], and the loss means stay global."""
-    lst = [int(i) for i in idxs]
-    return lst[rank::world], len(lst), sum(1 for i in lst if i > 0)
+    """This rank's slice of a batch plus the global normalisers: every rank draws the same batches (same CPU RNG state,
+    see _sync_cpu_rng) and the loss means stay global.  The batch is SORTED by frame index and cut into contiguous
+    slices: UVT row ids are assigned in frame order (flow-tracked pixels inherit, new pixels get fresh consecutive ids),
+    so a frame's rows cluster in the row range of shard ~ frame * world / N, and rank r, which owns that range, mostly
+    gathers from / reduces into its own memory instead of a peer's."""
+    lst = sorted(int(i) for i in idxs)
+    n = len(lst)
+    return lst[rank * n // world:(rank + 1) * n // world], n, sum(1 for i in lst if i > 0)
 
 
 def _sync_cpu_rng(device):
