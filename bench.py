@@ -42,6 +42,7 @@ def parse():
     p.add_argument("--width", type=int, default=1280)
     p.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-ref-on-b200", action="store_true")
     p.add_argument("--stage2-iters", type=int, default=20)
     return p.parse_args()
 
@@ -104,29 +105,87 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port timed on the host cores
+# The reference's PyTorch op sequence (oracle/unet_ref.py + the oracle VidToMe patch), used as the BASELINE that is
+# timed, never as the product: on the host cores (cpu_baseline / --impl reference) and on the B200 itself
+# (reference_on_b200: cuDNN / cuBLAS / SDPA with materialised VidToMe scores).
 # ----------------------------------------------------------------------------------------------
-def cpu_sample(h, w, repeats=1, warm=0):
-    """One xy chunk-forward of a single frame (CFG pair = 2 images, text L=154) through the oracle
-    UNet (torch fp32, all host threads).  Returns seconds per sample."""
+class SdpaFlops:
+    """torch's FlopCounterMode does not see the CPU scaled_dot_product_attention: count 4*B*H*Tq*Tk*d here."""
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self.F, self.orig, self.flops = F, F.scaled_dot_product_attention, 0.0
+
+        def counted(q, k, v, *a, **kw):
+            self.flops += 4.0 * q.shape[0] * q.shape[1] * q.shape[2] * k.shape[2] * q.shape[3]
+            return self.orig(q, k, v, *a, **kw)
+
+        F.scaled_dot_product_attention = counted
+        return self
+
+    def __exit__(self, *exc):
+        self.F.scaled_dot_product_attention = self.orig
+
+
+def oracle_chunks(device, dtype, h, w, plane, seed=0):
+    """Returns run(k): the k-th chunk-forward of one denoising step through the oracle UNet with the oracle ToMe patch
+    (xy: 4 frames of h x w, L=154; yt: 4 latent columns as 64 x h 'images', L=77), CFG pair, guidance 2.0.  Chunk 0 has no
+    global-token pool, later chunks merge against it (the steady state of a pass)."""
     import torch
-    from oracle.unet_ref import make_unet
+    from oracle import pipeline_ref as P
+    from oracle.unet_ref import apply_oracle_patch, make_unet, reset_oracle_pool
+
+    unet = make_unet(seed=0).to(device=device, dtype=dtype)
+    apply_oracle_patch(unet, 0.6, True, 0.5, global_rand=0.5)
+    g = torch.Generator().manual_seed(seed)
+    ih, iw = (h, w) if plane == "xy" else (64, h)
+    L = 154 if plane == "xy" else 77
+    x = torch.randn(1, 4, ih, iw, generator=g).repeat(12, 1, 1, 1).to(device=device, dtype=dtype)
+    cc = (0.18215 * (torch.randn(1, 4, ih, iw, generator=g) + 0.02 * torch.randn(12, 4, ih, iw, generator=g))).to(device=device, dtype=dtype)
+    text = torch.randn(2, L, 768, generator=g).to(device=device, dtype=dtype)
+    t = torch.tensor(801, device=device)
+
+    def run(k):
+        sl = slice(4 * (k % 3), 4 * (k % 3) + 4)
+        with torch.no_grad():
+            return P.cfg_noise(unet, x[sl], text, t, cc[sl], 2.0)
+
+    run.reset = lambda: reset_oracle_pool(unet)
+    return run
+
+
+def cpu_path1_sample(h, w):
+    """Two consecutive 4-frame xy chunk-forwards (without / with the global-token pool) of the oracle UNet + ToMe patch in
+    fp32 on all host threads.  Returns (seconds, TFLOP executed)."""
+    import torch
+    from torch.utils.flop_counter import FlopCounterMode
 
     torch.set_num_threads(os.cpu_count() or 1)
-    unet = make_unet(seed=0)
-    g = torch.Generator().manual_seed(0)
-    x = torch.randn(1, 4, h, w, generator=g)
-    cc = torch.randn(1, 4, h, w, generator=g) * 0.18215
-    text = torch.randn(2, 154, 768, generator=g)
-    t = torch.tensor(801)
-    times = []
-    with torch.no_grad():
-        for i in range(warm + repeats):
-            t0 = time.perf_counter()
-            unet(torch.cat([x, x]), t, encoder_hidden_states=text, cross_attention_kwargs={"concat_conds": cc})
-            if i >= warm:
-                times.append(time.perf_counter() - t0)
-    return times
+    run = oracle_chunks("cpu", torch.float32, h, w, "xy")
+    with SdpaFlops() as sd, FlopCounterMode(display=False) as fc:
+        t0 = time.perf_counter()
+        run(0)
+        run(1)
+        sec = time.perf_counter() - t0
+    return sec, (fc.get_total_flops() + sd.flops) / 1e12
+
+
+def cpu_stage2_sample(H, W, frames=16, iters=2):
+    """Stage-2 iterations of the oracle optimiser (torch autograd, the reference's op sequence) on the host cores: a
+    `frames`-frame clip at the bench resolution, batch 16.  Returns seconds per iteration (init subtracted)."""
+    import torch
+    from oracle import postopt_ref as O
+    from tclight_b200.postopt import synthetic_workload
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    edited, flows, masks, inv = synthetic_workload(frames, H, W, "cpu")
+    batch = [list(range(min(16, frames)))]
+    t0 = time.perf_counter()
+    O.stage2_uvt(edited, flows, masks, inv, [batch])
+    t1 = time.perf_counter()
+    O.stage2_uvt(edited, flows, masks, inv, [batch * (1 + iters)])
+    t2 = time.perf_counter()
+    return max(((t2 - t1) - (t1 - t0)) / iters, 1e-9)
 
 
 def step_units(frames, w_lat, win=64, chunk=4):
@@ -137,14 +196,35 @@ def step_units(frames, w_lat, win=64, chunk=4):
     return n_xy, n_yt
 
 
-def cpu_extrapolate(sec_per_sample, frames, h, w):
-    """steps/s of a full multi-axis step, extrapolated from the single-frame sample by the FLOP
-    model (scaled by pixel count when not at 720x1280)."""
+def step_tflop_model(frames, h, w):
+    """TFLOP of one full multi-axis step by the FLOP model of SURVEY.md §8(d) (scaled by pixel count off 720x1280)."""
     n_xy, n_yt = step_units(frames, w)
     px = (h * w) / (90.0 * 160.0)
-    step_tf = (n_xy * XY_CHUNK_TF + n_yt * YT_CHUNK_TF * (min(frames, 64) / 64.0)) * px
-    sample_tf = 2 * PLAIN_IMAGE_TF * px
-    return 1.0 / (sec_per_sample * step_tf / sample_tf), step_tf / sample_tf
+    return (n_xy * XY_CHUNK_TF + n_yt * YT_CHUNK_TF * (min(frames, 64) / 64.0)) * px
+
+
+def cpu_baseline(args, step_tflop=None, with_stage2=True):
+    """The reference's CPU path timed on this box's host cores, on a bounded sample: the denoising path as TFLOP/s of real
+    4-frame xy chunk-forwards with the ToMe patch at HALF the latent resolution (a full-resolution chunk-forward is ~64
+    TFLOP, minutes on a CPU), converted to steps/s with the step's FLOPs; stage 2 as it/s of the oracle optimiser."""
+    h, w = args.height // 8, args.width // 8
+    hs, ws = max(h // 2, 16), max(w // 2, 16)
+    sec, tf = cpu_path1_sample(hs, ws)
+    rate = tf / sec
+    step_tf = step_tflop if step_tflop else step_tflop_model(args.frames, h, w)
+    out = {"value": rate / step_tf, "unit": "steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+           "sample": (f"oracle UNet + ToMe patch fp32: two 4-frame xy chunk-forwards (no pool / pool) at latent {hs}x{ws} = {tf:.2f} TFLOP in "
+                      f"{sec:.1f} s = {rate:.3f} TFLOP/s; one full step = {step_tf:.0f} TFLOP"
+                      f" ({'counted from the B200 arm launches' if step_tflop else 'FLOP model of SURVEY.md 8d'})"),
+           "path1_cpu_tflops": rate}
+    if with_stage2:
+        try:
+            s_it = cpu_stage2_sample(args.height, args.width)
+            out["stage2"] = {"value": 1.0 / s_it, "unit": "it/s",
+                             "sample": f"oracle stage-2 optimiser (torch autograd fp32), 16 frames at {args.height}x{args.width}, batch 16, 2 iterations"}
+        except Exception as ex:  # noqa: BLE001
+            out["stage2"] = {"value": None, "error": str(ex)[:200]}
+    return out
 
 
 def run_reference(args):
@@ -152,23 +232,111 @@ def run_reference(args):
     if rank != 0:
         return
     h, w = args.height // 8, args.width // 8
-    times = cpu_sample(h, w, repeats=max(1, args.steps), warm=min(args.warmup, 1))
-    sec = sum(times) / len(times)
-    sps, ratio = cpu_extrapolate(sec, args.frames, h, w)
+    hs, ws = max(h // 2, 16), max(w // 2, 16)
+    step_tf = step_tflop_model(args.frames, h, w)
+    rates, secs = [], []
+    for i in range(min(args.warmup, 1) + max(1, min(args.steps, 4))):      # each "step" = one bounded sample; capped to stay in minutes
+        sec, tf = cpu_path1_sample(hs, ws)
+        if i >= min(args.warmup, 1):
+            rates.append(tf / sec)
+            secs.append(sec)
+    rate = sum(rates) / len(rates)
+    sps = rate / step_tf
     cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": "denoising_steps_per_sec", "value": sps, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / sps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.frames}f@{args.height}x{args.width} multi-axis denoising + VidToMe (chunk 4, mix-4, 0.6/0.5), L=154/77, guidance 2.0",
-                   "unit_def": "step = one full-video multi-axis denoising step",
-                   "note": "reference is Python/PyTorch: timed = oracle port of its CPU path (oracle/unet_ref.py), bounded sample extrapolated by the FLOP model"},
+        "config": workload_config(args),
         "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": f"1-frame xy chunk-forward (2 images, L=154) = {sec:.2f} s; extrapolated x{ratio:.0f} by the FLOP model"},
+                         "sample": (f"oracle UNet + ToMe patch fp32: two 4-frame xy chunk-forwards (no pool / pool) at latent {hs}x{ws}, "
+                                    f"{len(rates)} sample(s) of {sum(secs) / len(secs):.1f} s = {rate:.3f} TFLOP/s; one full step = {step_tf:.0f} TFLOP "
+                                    "(FLOP model of SURVEY.md 8d)")},
         "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:
+        s_it = cpu_stage2_sample(args.height, args.width)
+        line["stage2"] = {"metric": "stage2_iters_per_sec", "value": 1.0 / s_it, "unit": "it/s",
+                          "sample": f"oracle stage-2 optimiser (torch autograd fp32), 16 frames at {args.height}x{args.width}, batch 16, 2 iterations"}
+    except Exception as ex:  # noqa: BLE001
+        line["stage2"] = {"value": None, "error": str(ex)[:200]}
     print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    """Identical for both arms (the driver compares the two lines' configs)."""
+    h, w = args.height // 8, args.width // 8
+    n_xy, n_yt = step_units(args.frames, w)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return {"workload": f"{args.frames}f@{args.height}x{args.width} multi-axis denoising + VidToMe (chunk 4, mix-4, 0.6/0.5), L=154/77, guidance 2.0",
+            "unit_def": "step = one full-video multi-axis denoising step", "xy_chunk_forwards_per_step": n_xy,
+            "yt_chunk_forwards_per_step": n_yt,
+            "parallelism": f"frame/column shards x{world}, all-reduce of noises" if world > 1 else "single GPU",
+            "l2": "inputs larger than L2 (activations of one chunk-forward exceed 126 MB)", "weights": "seeded random, SD-1.5 shapes (860M)"}
+
+
+def tracked_traffic():
+    """dram bytes per launch of the roofline kernels, read from the tracked ncu summary (profiles/traffic.json, written by
+    tools/ncu_traffic.py from the committed ncu csv) instead of a literal."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def reference_on_b200(dev, dtype, h, w, frames, n_xy, n_yt, mine_xy_ms, mine_yt_ms):
+    """The reference's PyTorch path on this B200: steady-state xy and yt chunk-forwards of the oracle
+    UNet + ToMe patch (cuDNN convs, cuBLAS linears, SDPA attention, materialised matching scores) in the bench dtype, CUDA
+    events, extrapolated to a step by the call counts."""
+    import torch
+
+    out = {}
+    for plane, n_calls in (("xy", n_xy), ("yt", n_yt)):
+        try:
+            run = oracle_chunks(dev, dtype, h, w, plane)
+            run(0); run(1)                      # warm-up: cuDNN autotune, pool built
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            run(2); run(0)
+            e.record()
+            torch.cuda.synchronize()
+            out[plane + "_chunk_forward_ms"] = s.elapsed_time(e) / 2
+            del run
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            out[plane + "_error"] = str(ex)[:200]
+    if "xy_chunk_forward_ms" in out and "yt_chunk_forward_ms" in out:
+        step_ms = n_xy * out["xy_chunk_forward_ms"] + n_yt * out["yt_chunk_forward_ms"]
+        out.update({"steps_per_sec": 1e3 / step_ms, "ms_per_step": step_ms,
+                    "this_repo_xy_chunk_forward_ms": mine_xy_ms, "this_repo_yt_chunk_forward_ms": mine_yt_ms,
+                    "note": "oracle/unet_ref.py + oracle ToMe patch on CUDA (library kernels), steady-state chunk-forwards x call counts; "
+                            "sampler / AdaIN / scheduler time not included on the reference side"})
+    return out
+
+
+def reference_stage2_on_b200(dev, H, W, frames=16, iters=3):
+    """torch-autograd stage-2 iterations (oracle/postopt_ref.py, the reference's op sequence) on this B200."""
+    import torch
+    from oracle import postopt_ref as O
+    from tclight_b200.postopt import synthetic_workload
+
+    edited, flows, masks, inv = synthetic_workload(frames, H, W, dev)
+    batch = [list(range(min(16, frames)))]
+
+    def timed(k):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        O.stage2_uvt(edited, flows, masks, inv, [batch * k])
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    timed(1)
+    a, b = timed(1), timed(1 + iters)
+    return {"value": iters / max(b - a, 1e-9), "unit": "it/s",
+            "sample": f"torch autograd fp32 on CUDA, {frames} frames at {H}x{W}, batch 16 (Adam over that clip's U rows only)"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -280,33 +448,44 @@ def run_b200(args):
     clocks = clk.stop() if rank == 0 else None
     finite = bool(torch.isfinite(state["x"].float()).all().item())
 
+    # the two plane passes on their own (xy and yt chunk-forwards/s separately)
+    t_mid = timesteps[len(timesteps) // 2]
+    ms_xy = timed(lambda: (gen.pre_iter(state["x"], t_mid), gen.xy_pass(state["x"], conds, t_mid, state["cc"], state["noises"]),
+                           gen.post_iter(state["x"], t_mid)), 1)
+    ms_yt = timed(lambda: (gen.pre_iter(state["x"], t_mid), gen.yt_pass(state["x"], conds_t, t_mid, state["cc"], state["noises_t"]),
+                           gen.post_iter(state["x"], t_mid)), 1)
+
     pk, pk_kind = peaks()
+    traffic = tracked_traffic()
     n_xy, n_yt = step_units(N, w)
     sps = args.steps / (ms * 1e-3)
     sps_e2e = args.steps / (ms_e2e * 1e-3)
-    # dominant kernel: ds-1 self-attention (attn_kernel<2,64,..>): algorithmic FLOPs / event time
+    # dominant kernel: ds-1 self-attention: algorithmic FLOPs / event time
     a = prof.get("attention_d64", {"flops": 0.0, "ms": 0.0, "launches": 0})
     roof = None
     if a["ms"] > 0:
         ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "attn_kernel<NQ=2,DPAD=64,TS,POLY=0x03> (ds-1 self/cross attention)", "achieved": ach,
+        tr = traffic.get("attention_ds1", {})
+        roof = {"bound": "tensor", "kernel": "attn_kernel (ds-1 self/cross attention, head dim 40)", "achieved": ach,
                 "peak": pk["bf16_tflops_sustained"], "peak_kind": f"{pk_kind} sustained bf16", "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops_sustained"],
-                # dram__bytes_read+write of ONE launch of this kernel at its largest shape (ds-1 merged xy self-attention,
-                # B*H=16, T=47 520): profiles/r01_attention_v2_ncu_summary.md; algorithmic Q,K,V^T,O bytes of that launch: 353 MB
-                "traffic": 347.0e6, "traffic_unit": "bytes/launch (ncu --set full, largest launch shape)",
+                "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+                "traffic_unit": "bytes/launch (ncu dram__bytes_read+write, largest launch shape: merged xy self-attention, T=47520)",
                 "launches": a["launches"], "avg_launch_ms": a["ms"] / max(1, a["launches"]),
                 "share_of_step": a["ms"] / ms}
     total_fl = sum(v["flops"] for v in prof.values())
+    cfgd = workload_config(args)
     line = {
         "metric": "denoising_steps_per_sec", "value": sps, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"{N}f@{H}x{W} multi-axis denoising + VidToMe (chunk 4, mix-4, 0.6/0.5), L=154/77, guidance 2.0",
-                   "unit_def": "step = one full-video multi-axis denoising step", "xy_chunk_forwards_per_step": n_xy,
-                   "yt_chunk_forwards_per_step": n_yt, "parallelism": f"frame/column shards x{world}, all-reduce of noises" if world > 1 else "single GPU",
-                   "l2": "inputs larger than L2 (activations of one chunk-forward exceed 126 MB)", "weights": "seeded random, SD-1.5 shapes (860M)"},
+        "config": cfgd,
         "chunk_forwards_per_sec": (n_xy + n_yt) * sps,
+        "xy_pass": {"ms": ms_xy, "chunk_forwards": n_xy, "chunk_forwards_per_sec": n_xy / (ms_xy * 1e-3)},
+        "yt_pass": {"ms": ms_yt, "chunk_forwards": n_yt, "chunk_forwards_per_sec": n_yt / (ms_yt * 1e-3)},
+        # per-rank path FLOPs: with shards the first chunk of every shard has no pool yet, so N ranks do slightly LESS attention
+        # work than one (the driver's scaling efficiency should be read next to these)
+        "path_tflop_per_step_all_ranks": None,
         "path_tflops": total_fl * world / (ms * 1e-3) / 1e12 if total_fl else None,
         "path_frac_of_sustained_bf16": (total_fl / (ms * 1e-3) / 1e12) / pk["bf16_tflops_sustained"] if total_fl else None,
         "kernel_breakdown_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
@@ -315,24 +494,61 @@ def run_b200(args):
                 "d2h_bytes_per_step": int(x_host.numel() * x_host.element_size())},
         "gpu_launches": int(launches.item()), "clocks": clocks, "finite": finite,
     }
+    fl_t = torch.tensor([total_fl / max(1, args.steps)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(fl_t)
+    line["path_tflop_per_step_all_ranks"] = fl_t.item() / 1e12
+    # free the denoising state before the other legs
+    del state, unet, gen, pipe
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_ref_on_b200:
+        try:
+            line["reference_on_b200"] = reference_on_b200(dev, adt, h, w, N, n_xy, n_yt, ms_xy / n_xy, ms_yt / n_yt)
+        except Exception as ex:  # noqa: BLE001
+            line["reference_on_b200"] = {"error": str(ex)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            times = cpu_sample(h, w, repeats=1, warm=0)
-            v, ratio = cpu_extrapolate(times[0], N, h, w)
-            line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"oracle UNet fp32, 1-frame xy chunk-forward (2 images) = {times[0]:.2f} s, extrapolated x{ratio:.0f} by FLOP model"}
+            line["cpu_baseline"] = cpu_baseline(args, step_tflop=line["path_tflop_per_step_all_ranks"] or None)
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
-    try:
+    if args.stage2_iters > 0:
         from tclight_b200 import postopt
-        if hasattr(postopt, "bench_stage2") and args.stage2_iters > 0:
-            line["stage2"] = postopt.bench_stage2(dev, N if world == 1 else N, H, W, iters=args.stage2_iters, rank=rank, world=world)
-    except ImportError:
-        pass
+        line["stage2"], line["stage1"] = postopt.bench_postopt(dev, N, H, W, iters=args.stage2_iters, rank=rank, world=world,
+                                                               traffic=traffic.get("stage2_iteration", {}))
+        if rank == 0 and world == 1 and not args.no_ref_on_b200:
+            try:
+                line["stage2"]["reference_on_b200"] = reference_stage2_on_b200(dev, H, W)
+                line["stage2"]["convergence_vs_oracle"] = stage2_convergence_vs_oracle(dev)
+            except Exception as ex:  # noqa: BLE001
+                line["stage2"]["reference_on_b200"] = {"error": str(ex)[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def stage2_convergence_vs_oracle(dev):
+    """The full reference budget (70 epochs) of stage 2 on a down-scaled clip through this repo's optimiser and through the
+    oracle (torch autograd), same batches: loss-curve end points side by side."""
+    import types
+
+    import torch
+    from oracle import postopt_ref as O
+    from tclight_b200.postopt import OptDataset, unique_tensor_optimization
+
+    n, hh, ww, bo, epochs = 16, 176, 192, 8, 70
+    edited, flows, masks, inv = O.synthetic_clip(n=n, h=hh, w=ww, seed=1, device=dev)
+    ds = OptDataset(edited.clone(), flows, masks, device=dev)
+    gen = types.SimpleNamespace(dataset=ds, data_parser=types.SimpleNamespace(unq_inv=inv), lambda_dssim=0.2, lambda_flow=0.8,
+                                lambda_tv=0.05, epochs_exposure=0, epochs=epochs, opt_batch_size=bo, feature_lr=0.05,
+                                exposure_lr_init=0.01, exposure_lr_final=0.001, exposure_lr_delay_steps=0, exposure_lr_delay_mult=0.0)
+    torch.manual_seed(7)
+    _, got = unique_tensor_optimization(gen)
+    torch.manual_seed(7)
+    _, _, want = O.stage2_uvt(edited, flows, masks, inv, O.draw_batches(n, bo, epochs), feature_lr=0.05)
+    return {"clip": f"{n} frames {hh}x{ww}, batch {bo}, {epochs} epochs = {len(got)} iterations",
+            "loss_first": [got[0], want[0]], "loss_last": [got[-1], want[-1]], "order": "[this repo, oracle]",
+            "max_abs_diff_over_curve": max(abs(a - b) for a, b in zip(got, want))}
 
 
 if __name__ == "__main__":

@@ -402,11 +402,15 @@ def synthetic_workload(n_frames: int, H: int, W: int, device, track_len: int = 1
     return edited, flows, masks, unq_inv
 
 
-def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: int = 0, world: int = 1, batch: int = 16):
-    """Times `iters` stage-2 iterations (16 frames each) at the named shape; returns a dict for the
-    bench JSON line.  Algorithmic bytes per iteration: 80*Bo*P + 84*U."""
+def bench_postopt(device, n_frames: int, H: int, W: int, iters: int = 20, rank: int = 0, world: int = 1, batch: int = 16,
+                  traffic=None, full_budget: bool = True):
+    """Stage-2 / stage-1 measurements at the named shape for the bench JSON line: (1) `iters` stage-2 iterations (16
+    frames each) timed with CUDA events; (2) the reference's full budget (70 epochs of stage 2, 35 of stage 1) through
+    the public API, loss curve end points.  Algorithmic bytes per stage-2 iteration: 80*Bo*P + 84*U.
+    Returns (stage2 dict, stage1 dict)."""
     import json
     import os
+    import time
     import types
 
     edited, flows, masks, unq_inv = synthetic_workload(n_frames, H, W, device)
@@ -416,7 +420,6 @@ def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: i
     Bo = batch
     ids = unq_inv.to(torch.int32).contiguous()
     U = int(unq_inv.max().item()) + 1
-    del unq_inv
     ctx = _Context(ds, 0.2, 0.8, 0.05, Bo)
     fdc = torch.empty((U, 3), device=device, dtype=torch.float32)
     cnt = torch.empty(U, device=device, dtype=torch.float32)
@@ -455,6 +458,13 @@ def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: i
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], device=device, dtype=torch.float64)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     run(3, 0)
     sync()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -462,13 +472,16 @@ def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: i
     run(iters, 3)
     e.record()
     sync()
-    ms_t = torch.tensor([s.elapsed_time(e) / iters], device=device)
+    ms = max_over_ranks(s.elapsed_time(e) / iters)
     if world > 1:
         import torch.distributed as dist
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(losses)
         tab.close()
-    ms = ms_t.item()
+    loss_fl = [losses[3, 0].item(), losses[(3 + iters - 1) % len(losses), 0].item()]
+    del m, v, tab, ctx
+    if world == 1:
+        del fdc, grad
+    torch.cuda.empty_cache()
     P_ = H * W
     alg_bytes = 80.0 * Bo * P_ + 84.0 * U
     try:
@@ -478,10 +491,44 @@ def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: i
     except Exception:
         peak, kind = 6650.0, "fallback"
     ach = alg_bytes / (ms * 1e-3) / 1e9
-    return {"metric": "stage2_iters_per_sec", "value": 1e3 / ms, "unit": "it/s", "ms_per_iter": ms, "frames": N, "batch": Bo,
-            "U": U, "U_over_NP": U / (N * P_), "algorithmic_bytes_per_iter": alg_bytes,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": kind, "unit": "GB/s", "frac": ach / peak, "traffic": None},
-            "loss_first_last": [losses[3, 0].item(), losses[(3 + iters - 1) % len(losses), 0].item()], "n_gpus": world,
-            "parallelism": (f"batch-parallel x{world}; UVT rows + gradient sharded by row range, gathered / reduced through peer memory over "
-                            "NVLink inside the gather and level-0 kernels, Adam on the local shard") if world > 1 else "single GPU",
-            "note": "dense-Adam semantics (every UVT row updated every iteration, as torch.optim.Adam does)"}
+    traffic = traffic or {}
+    s2 = {"metric": "stage2_iters_per_sec", "value": 1e3 / ms, "unit": "it/s", "ms_per_iter": ms, "frames": N, "batch": Bo,
+          "U": U, "U_over_NP": U / (N * P_), "algorithmic_bytes_per_iter": alg_bytes,
+          "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": kind, "unit": "GB/s", "frac": ach / peak,
+                       "traffic": traffic.get("dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
+                       "traffic_unit": "bytes/iteration (ncu dram__bytes_read+write summed over the iteration's kernels, 1 GPU)"},
+          "loss_first_last": loss_fl, "n_gpus": world,
+          "parallelism": (f"batch-parallel x{world}; UVT rows + gradient sharded by row range, gathered / reduced through peer memory over "
+                          "NVLink inside the gather and level-0 kernels, Adam on the local shard") if world > 1 else "single GPU",
+          "note": "dense-Adam semantics (every UVT row updated every iteration, as torch.optim.Adam does)"}
+    s1 = {}
+    if full_budget:
+        gen = types.SimpleNamespace(dataset=ds, data_parser=types.SimpleNamespace(unq_inv=unq_inv), lambda_dssim=0.2, lambda_flow=0.8,
+                                    lambda_tv=0.05, epochs_exposure=35, epochs=70, opt_batch_size=Bo, feature_lr=0.05,
+                                    exposure_lr_init=0.01, exposure_lr_final=0.001, exposure_lr_delay_steps=0,
+                                    exposure_lr_delay_mult=0.0, _world=world, _rank=rank)
+        torch.manual_seed(12345)
+        sync()
+        t0 = time.perf_counter()
+        _, curve = unique_tensor_optimization(gen)
+        sync()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        s2["full_budget"] = {"epochs": 70, "iterations": len(curve), "seconds": dt, "iters_per_sec": len(curve) / dt,
+                             "loss_first": curve[0], "loss_last": curve[-1], "loss_min": min(curve),
+                             "note": "Generator.unique_tensor_optimization: the reference's iteration budget (generate.py:453-533) through the "
+                                     "public API, DataLoader draws and UVT init / final render included (wall clock)"}
+        torch.manual_seed(12345)
+        sync()
+        t0 = time.perf_counter()
+        _, curve1 = exposure_align(gen)
+        sync()
+        dt1 = max_over_ranks(time.perf_counter() - t0)
+        s1 = {"metric": "stage1_iters_per_sec", "value": len(curve1) / dt1, "unit": "it/s", "epochs": 35, "iterations": len(curve1),
+              "seconds": dt1, "loss_first": curve1[0], "loss_last": curve1[-1], "n_gpus": world,
+              "parallelism": f"batch-parallel x{world}, NCCL all-reduce of the [N,12] exposure gradient" if world > 1 else "single GPU",
+              "note": "Generator.exposure_align (generate.py:354-451) through the public API (wall clock)"}
+    return s2, s1
+
+
+def bench_stage2(device, n_frames: int, H: int, W: int, iters: int = 20, rank: int = 0, world: int = 1, batch: int = 16):
+    return bench_postopt(device, n_frames, H, W, iters=iters, rank=rank, world=world, batch=batch, full_budget=False)[0]
