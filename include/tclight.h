@@ -248,8 +248,8 @@ typedef struct {
   const float* edited;     /* [N,3,H,W] OptDataset.edited_images                            */
   const float* past_flows; /* [N,2,H,W]                                                      */
   const float* mask_bwd;   /* [N,1,H,W] soft masks                                           */
-  const float* ypyr;       /* target pyramid from tcl_postopt_build_pyramid:
-                              [N,3,tcl_postopt_pyramid_elems(H,W)]                           */
+  const float* ypyr;       /* target side from tcl_postopt_build_pyramid (pyramid levels 1..4 and the
+                              constant SSIM maps G*y, G*y^2): [N,3,tcl_postopt_target_elems(H,W)] */
   float lambda_dssim, lambda_flow, lambda_tv;
   int32_t max_batch;       /* largest n_batch that will be used with this workspace          */
   int32_t norm_batch;      /* data parallel: GLOBAL batch size the loss means are taken over
@@ -262,6 +262,7 @@ typedef struct {
 
 size_t tcl_postopt_workspace_bytes(int H, int W, int max_batch);
 long long tcl_postopt_pyramid_elems(int H, int W);
+long long tcl_postopt_target_elems(int H, int W);
 int tcl_postopt_build_pyramid(const float* edited, int N, int H, int W, float* ypyr, tcl_stream_t stream);
 int tcl_uvt_iteration(const tcl_postopt_ctx* ctx, const int* idx_host, int n_batch, const int* ids, long long U,
                       float* fdc, float* grad, float* m, float* v, float lr, float beta1, float beta2, float eps,

@@ -216,6 +216,8 @@ lib.tcl_postopt_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
 lib.tcl_postopt_workspace_bytes.restype = C.c_size_t
 lib.tcl_postopt_pyramid_elems.argtypes = [C.c_int, C.c_int]
 lib.tcl_postopt_pyramid_elems.restype = C.c_longlong
+lib.tcl_postopt_target_elems.argtypes = [C.c_int, C.c_int]
+lib.tcl_postopt_target_elems.restype = C.c_longlong
 lib.tcl_postopt_build_pyramid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 lib.tcl_postopt_build_pyramid.restype = C.c_int
 lib.tcl_uvt_iteration.argtypes = [C.POINTER(PostoptCtx), C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_longlong,

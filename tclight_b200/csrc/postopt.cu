@@ -95,42 +95,55 @@ struct LevelPlan {
   int planes;
 };
 
-struct SsimMaps { float mu1, mu2, e11, e22, e12; };
-
-// dst[m][r][c] = sum_k g[k] src[m][r + k][c]   (r < ST, c < SR), strips of 8 rows
-template <int NM, typename F>
-__device__ __forceinline__ void filt_vertical(F load /* (m, row, col) -> float */, float (*dst)[ST][SPITCH]) {
-  for (int t = threadIdx.x; t < NM * 4 * SR; t += blockDim.x) {
-    const int m = t / (4 * SR);
-    const int rem = t - m * 4 * SR;
-    const int strip = rem / SR, cc = rem - strip * SR;
-    float acc[8];
+// The 11-tap filters run on packed fp32x2 FMAs (Blackwell FFMA2: two outputs per issue slot — these kernels are bound by
+// FMA issue, not by memory).  Outputs are handled in adjacent pairs (o, o+1): an input at distance k from output o is at
+// distance k-1 from output o+1, so the weight pair is gp[k] = (g[k], g[k-1]) with g[-1] = g[11] = 0.  Each output still
+// accumulates its 11 products in ascending tap order, exactly like the scalar loop.
+struct GaussPairs { float2 gp[12]; };
+__device__ __forceinline__ void load_gauss_pairs(GaussPairs& G) {
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 18; ++i) {
-      const float vin = load(m, strip * 8 + i, cc);
-#pragma unroll
-      for (int o = 0; o < 8; ++o)
-        if (i - o >= 0 && i - o < 11) acc[o] += c_gauss[i - o] * vin;
-    }
-#pragma unroll
-    for (int o = 0; o < 8; ++o) dst[m][strip * 8 + o][cc] = acc[o];
-  }
+  for (int k = 0; k < 12; ++k) G.gp[k] = make_float2(k <= 10 ? c_gauss[k] : 0.f, k >= 1 ? c_gauss[k - 1] : 0.f);
 }
 
-// out[o] = sum_k g[k] src[r][c0 + o + k], o < 4
-__device__ __forceinline__ void filt_row4(const float* src_row, float (&out)[4]) {
-  float in[14];
+// vertical pass of one thread: 8 outputs (rows strip*8 .. +7) of NM maps at column cc from 18 input rows.
+//   val(i, v[NM]) produces the NM map values of input row i;  dst[m][row][cc] receives the outputs.
+template <int NM, typename F>
+__device__ __forceinline__ void vstrip8(const GaussPairs& G, F val, float (*dst)[ST][SPITCH], int strip, int cc) {
+  float2 acc[4][NM];
 #pragma unroll
-  for (int i = 0; i < 14; ++i) in[i] = src_row[i];
+  for (int q = 0; q < 4; ++q)
 #pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    float a = 0.f;
+    for (int m = 0; m < NM; ++m) acc[q][m] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < 11; ++k) a += c_gauss[k] * in[o + k];
-    out[o] = a;
+  for (int i = 0; i < 18; ++i) {
+    float v[NM];
+    val(i, v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = i - 2 * q;             // distance to the pair's first output
+      if (k >= 0 && k <= 11) {
+#pragma unroll
+        for (int m = 0; m < NM; ++m) acc[q][m] = __ffma2_rn(G.gp[k], make_float2(v[m], v[m]), acc[q][m]);
+      }
+    }
   }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int m = 0; m < NM; ++m) { dst[m][strip * 8 + 2 * q][cc] = acc[q][m].x; dst[m][strip * 8 + 2 * q + 1][cc] = acc[q][m].y; }
+}
+
+// horizontal pass: out[o] = sum_k g[k] src_row[o + k], o < 4
+__device__ __forceinline__ void hrow4(const GaussPairs& G, const float* src_row, float (&out)[4]) {
+  float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < 14; ++t) {
+    const float v = src_row[t];
+    const float2 vv = make_float2(v, v);
+    if (t <= 11) a0 = __ffma2_rn(G.gp[t], vv, a0);
+    if (t >= 2) a1 = __ffma2_rn(G.gp[t - 2], vv, a1);
+  }
+  out[0] = a0.x; out[1] = a0.y; out[2] = a1.x; out[3] = a1.y;
 }
 
 __device__ __forceinline__ bool decode_block(const LevelPlan& lp, int& l, int& plane, int& ty0, int& tx0) {
@@ -148,13 +161,54 @@ __device__ __forceinline__ bool decode_block(const LevelPlan& lp, int& l, int& p
   return true;
 }
 
+// Target-side maps, constant over the optimisation (utils/loss_utils.py:104-113: mu2 = G*y, E[y^2] = G*(y*y)): computed once
+// per frame by tcl_postopt_build_pyramid and stored next to the pyramid, at the pyramid's offsets.
+__global__ void __launch_bounds__(256)
+ssim_target_kernel(float* __restrict__ Y, long long plane_stride, long long per, LevelPlan lp) {
+  __shared__ float sy[SR][SPITCH];
+  __shared__ float v[2][ST][SPITCH];
+  GaussPairs G;
+  load_gauss_pairs(G);
+  int l, plane, ty0, tx0;
+  decode_block(lp, l, plane, ty0, tx0);
+  const int h = lp.h[l], w = lp.w[l];
+  float* yp = Y + plane * plane_stride + lp.off[l];
+  const int oh = h - 10, ow = w - 10;
+  for (int i = threadIdx.x; i < SR * SR; i += blockDim.x) {
+    const int r = i / SR, cc = i - r * SR;
+    const int y = ty0 + r, x = tx0 + cc;
+    sy[r][cc] = (y < h && x < w) ? yp[(long long)y * w + x] : 0.f;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 4 * SR; t += blockDim.x) {
+    const int strip = t / SR, cc = t - strip * SR;
+    vstrip8<2>(G, [&](int i, float (&o)[2]) { const float yv = sy[strip * 8 + i][cc]; o[0] = yv; o[1] = yv * yv; }, v, strip, cc);
+  }
+  __syncthreads();
+  const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
+  float f[2][4];
+  hrow4(G, &v[0][r][c0], f[0]);
+  hrow4(G, &v[1][r][c0], f[1]);
+  const int py_ = ty0 + r;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int px_ = tx0 + c0 + o;
+    if (py_ < oh && px_ < ow) {
+      yp[per + (long long)py_ * w + px_] = f[0][o];
+      yp[2 * per + (long long)py_ * w + px_] = f[1][o];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 ssim_fwd_all_kernel(const float* __restrict__ X, long long x_plane_stride, const float* __restrict__ Y, long long y_frame_stride,
-                    long long y_chan_stride, Batch bt, LevelPlan lp, float C1, float C2, float* __restrict__ sums /*[4][planes][2]*/,
-                    float* __restrict__ pm /*[planes][3][pyr]*/, long long pm_map_stride) {
+                    long long y_chan_stride, long long y_per, Batch bt, LevelPlan lp, float C1, float C2,
+                    float* __restrict__ sums /*[4][planes][2]*/, float* __restrict__ pm /*[planes][3][pyr]*/, long long pm_map_stride) {
   __shared__ float sxy[2][SR][SPITCH];
-  __shared__ float v[5][ST][SPITCH];
+  __shared__ float v[3][ST][SPITCH];
   __shared__ float red[2][8];
+  GaussPairs G;
+  load_gauss_pairs(G);
   int l, plane, ty0, tx0;
   decode_block(lp, l, plane, ty0, tx0);
   const int h = lp.h[l], w = lp.w[l];
@@ -170,44 +224,30 @@ ssim_fwd_all_kernel(const float* __restrict__ X, long long x_plane_stride, const
     sxy[1][r][cc] = in ? yp[(long long)y * w + x] : 0.f;
   }
   __syncthreads();
-  // vertical (H) pass first, as pytorch_msssim.gaussian_filter does: maps x, y, x^2, y^2, xy share their 18 inputs
+  // vertical (H) pass first, as pytorch_msssim.gaussian_filter does: maps x, x^2, xy (the target-side maps are precomputed)
   for (int t = threadIdx.x; t < 4 * SR; t += blockDim.x) {
     const int strip = t / SR, cc = t - strip * SR;
-    float acc[8][5];
-#pragma unroll
-    for (int o = 0; o < 8; ++o)
-#pragma unroll
-      for (int m = 0; m < 5; ++m) acc[o][m] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 18; ++i) {
+    vstrip8<3>(G, [&](int i, float (&o)[3]) {
       const float xv = sxy[0][strip * 8 + i][cc], yv = sxy[1][strip * 8 + i][cc];
-      const float xx = xv * xv, yy = yv * yv, xy = xv * yv;
-#pragma unroll
-      for (int o = 0; o < 8; ++o)
-        if (i - o >= 0 && i - o < 11) {
-          const float g = c_gauss[i - o];
-          acc[o][0] += g * xv; acc[o][1] += g * yv; acc[o][2] += g * xx; acc[o][3] += g * yy; acc[o][4] += g * xy;
-        }
-    }
-#pragma unroll
-    for (int o = 0; o < 8; ++o)
-#pragma unroll
-      for (int m = 0; m < 5; ++m) v[m][strip * 8 + o][cc] = acc[o][m];
+      o[0] = xv; o[1] = xv * xv; o[2] = xv * yv;
+    }, v, strip, cc);
   }
   __syncthreads();
   float acc_cs = 0.f, acc_ss = 0.f;
   {
     const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
-    float f[5][4];
+    float f[3][4];
 #pragma unroll
-    for (int m = 0; m < 5; ++m) filt_row4(&v[m][r][c0], f[m]);
+    for (int m = 0; m < 3; ++m) hrow4(G, &v[m][r][c0], f[m]);
     const int py_ = ty0 + r;
     float* pm0 = pm + (long long)plane * 3 * pm_map_stride + lp.off[l] + (long long)py_ * w;
+    const float* ym = yp + y_per + (long long)py_ * w;
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       const int px_ = tx0 + c0 + o;
       if (py_ < oh && px_ < ow) {
-        const float mu1 = f[0][o], mu2 = f[1][o], e11 = f[2][o], e22 = f[3][o], e12 = f[4][o];
+        const float mu1 = f[0][o], e11 = f[1][o], e12 = f[2][o];
+        const float mu2 = ym[px_], e22 = ym[y_per + px_];
         const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
         const float A1 = 2.f * mu12 + C1, B1 = mu1_sq + mu2_sq + C1;
         const float s11 = e11 - mu1_sq, s22 = e22 - mu2_sq, s12 = e12 - mu12;
@@ -248,6 +288,8 @@ ssim_bwd_all_kernel(const float* __restrict__ X, long long x_plane_stride, const
                     const float* __restrict__ pm, long long pm_map_stride, float* __restrict__ own, long long own_plane_stride) {
   __shared__ float sp[3][SR][SPITCH];
   __shared__ float tt[3][ST][SPITCH];
+  GaussPairs G;
+  load_gauss_pairs(G);
   int l, plane, qy0, qx0;
   decode_block(lp, l, plane, qy0, qx0);
   const int h = lp.h[l], w = lp.w[l];
@@ -264,14 +306,18 @@ ssim_bwd_all_kernel(const float* __restrict__ X, long long x_plane_stride, const
   }
   __syncthreads();
   // transposed filters = the same correlations (the window is symmetric): dX(y) = sum_k g[k] pm(y - k)
-  filt_vertical<3>([&](int m, int r, int cc) { return sp[m][r][cc]; }, tt);
+  for (int t = threadIdx.x; t < 4 * SR; t += blockDim.x) {
+    const int strip = t / SR, cc = t - strip * SR;
+    vstrip8<3>(G, [&](int i, float (&o)[3]) { o[0] = sp[0][strip * 8 + i][cc]; o[1] = sp[1][strip * 8 + i][cc]; o[2] = sp[2][strip * 8 + i][cc]; },
+               tt, strip, cc);
+  }
   __syncthreads();
   const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
   const int y = qy0 + r;
   if (y < h) {
     float f[3][4];
 #pragma unroll
-    for (int m = 0; m < 3; ++m) filt_row4(&tt[m][r][c0], f[m]);
+    for (int m = 0; m < 3; ++m) hrow4(G, &tt[m][r][c0], f[m]);
     const float g_coef = coef[(size_t)(l - 1) * lp.planes + plane];
     const float* xp = X + plane * x_plane_stride + lp.off[l] + (long long)y * w;
     const float* yp = Y + bt.idx[b] * y_frame_stride + c * y_chan_stride + lp.off[l] + (long long)y * w;
@@ -1102,21 +1148,33 @@ using namespace tcl;
 extern "C" size_t tcl_postopt_workspace_bytes(int H, int W, int max_batch) { return ws_bytes(H, W, max_batch); }
 
 extern "C" long long tcl_postopt_pyramid_elems(int H, int W) { Pyr py; make_pyr(H, W, &py); return py.total; }
+extern "C" long long tcl_postopt_target_elems(int H, int W) { Pyr py; make_pyr(H, W, &py); return 3 * py.total; }
 
-// Target pyramid: ypyr[frame][channel][levels 1..4] from edited [N,3,H,W].
+// Target side of the photometric loss, built once: ypyr[frame][channel] = { levels 1..4 of the avg-pool pyramid | mu2 = G*y per
+// level | E[y^2] = G*(y*y) per level }, each tcl_postopt_pyramid_elems long (tcl_postopt_target_elems in total).
 extern "C" int tcl_postopt_build_pyramid(const float* edited, int N, int H, int W, float* ypyr, cudaStream_t stream) {
   TCL_CHECK_ARG(edited && ypyr && N > 0, "tcl_postopt_build_pyramid: args");
   Pyr py; make_pyr(H, W, &py);
   TCL_CHECK_ARG(py.h[4] >= 11 && py.w[4] >= 11, "tcl_postopt_build_pyramid: image too small for 5-level MS-SSIM (%dx%d)", H, W);
-  const int planes = N * 3;
+  int rc = ensure_gauss();
+  if (rc) return rc;
   const long long P = (long long)H * W;
+  const long long stride = 3 * py.total;
   for (int l = 0; l < 4; ++l) {
     const float* in = l == 0 ? edited : ypyr + py.off[l];
-    const long long in_stride = l == 0 ? P : py.total;
-    const long long total = (long long)planes * py.h[l + 1] * py.w[l + 1];
+    const long long in_stride = l == 0 ? P : stride;
+    const long long total = (long long)N * 3 * py.h[l + 1] * py.w[l + 1];
     avgpool2_kernel<<<gridp(total, 256), 256, 0, stream>>>(in, in_stride, py.h[l], py.w[l], py.ph[l], py.pw[l],
-                                                           ypyr + py.off[l + 1], py.total, py.h[l + 1], py.w[l + 1], planes);
+                                                           ypyr + py.off[l + 1], stride, py.h[l + 1], py.w[l + 1], N * 3);
     TCL_CHECK_LAUNCH("tcl_postopt_build_pyramid");
+  }
+  // a launch handles at most MAXB frames' worth of planes so that the block count stays well inside the grid limit
+  for (int f0 = 0; f0 < N; f0 += MAXB) {
+    const int nf = N - f0 < MAXB ? N - f0 : MAXB;
+    LevelPlan lp;
+    make_plan(py, nf * 3, true, 0, &lp);
+    ssim_target_kernel<<<lp.first[5], 256, 0, stream>>>(ypyr + (long long)f0 * 3 * stride, stride, py.total, lp);
+    TCL_CHECK_LAUNCH("tcl_postopt_build_pyramid(target maps)");
   }
   return TCL_OK;
 }
@@ -1204,8 +1262,8 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
   LevelPlan lpf, lpb;
   make_plan(py, planes, true, 0, &lpf);
   make_plan(py, planes, false, 0, &lpb);
-  ssim_fwd_all_kernel<<<lpf.first[5], 256, 0, stream>>>(w.xpyr, py.total, c->ypyr, 3 * py.total, py.total, bt, lpf, C1, C2, w.sums,
-                                                        w.pm, py.total);
+  ssim_fwd_all_kernel<<<lpf.first[5], 256, 0, stream>>>(w.xpyr, py.total, c->ypyr, 9 * py.total, 3 * py.total, py.total, bt, lpf, C1, C2,
+                                                        w.sums, w.pm, py.total);
   TCL_CHECK_LAUNCH("postopt(ssim_fwd)");
   // 4. loss head
   const int planes_g = nb_g * 3;
@@ -1213,7 +1271,7 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
   msssim_head_kernel<<<1, 64, 0, stream>>>(w.sums, planes, py, k_ms, w.coef, w.scal);
   TCL_CHECK_LAUNCH("postopt(head)");
   // 5. relaxed-SSIM backward, all levels in one launch
-  ssim_bwd_all_kernel<<<lpb.first[5], 256, 0, stream>>>(w.xpyr, py.total, c->ypyr, 3 * py.total, py.total, bt, lpb, w.coef, w.pm,
+  ssim_bwd_all_kernel<<<lpb.first[5], 256, 0, stream>>>(w.xpyr, py.total, c->ypyr, 9 * py.total, 3 * py.total, bt, lpb, w.coef, w.pm,
                                                         py.total, w.own, py.total);
   TCL_CHECK_LAUNCH("postopt(ssim_bwd)");
   own_collapse_kernel<<<gridp((long long)nb * py.h[1] * py.w[1], 256), 256, 0, stream>>>(w.own, py.total, py, nb, w.own1);

@@ -87,7 +87,7 @@ class _Context:
         if batch > L.TCL_POSTOPT_MAX_BATCH:
             raise TclError(f"post_opt.batch_size {batch} > {L.TCL_POSTOPT_MAX_BATCH}")
         self.N, self.H, self.W = N, H, W
-        per = lib.tcl_postopt_pyramid_elems(H, W)
+        per = lib.tcl_postopt_target_elems(H, W)
         self.ypyr = torch.empty((N, 3, per), device=e.device, dtype=torch.float32)
         check(lib.tcl_postopt_build_pyramid(e.data_ptr(), N, H, W, self.ypyr.data_ptr(), stream_ptr()), "tcl_postopt_build_pyramid")
         wsb = lib.tcl_postopt_workspace_bytes(H, W, batch)
