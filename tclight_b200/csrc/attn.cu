@@ -501,6 +501,302 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Persistent cross-attention on the text tokens (L = 154 or 77 -> 160 / 80 key columns; d_pad = 64, i.e. the ds-1 blocks
+// that carry 90 % of the cross-attention bytes).  HBM-bound: Q in, O out, nothing else.
+// One CTA per SM walks a contiguous range of (batch*head, Q tile) work items; the K / V^T tiles of the current
+// (text, head) stay resident in shared memory (39 KB) and are re-loaded only when the range crosses into another
+// (text, head); Q tiles stream through a 4-deep TMA ring; one TMEM allocation per CTA holds two {S|P, O} buffers, one
+// per softmax group, so softmax + epilogue of tile i overlap the MMAs of tile i+1.  Two issuer warps (Q K^T, P V) so that
+// neither kind of MMA waits behind the other's operands.
+// The softmax runs on 16 warps = FOUR threads per score row (warps w, w+4, w+8, w+12 share TMEM lanes 32*(w%4)...): each
+// thread holds a quarter of the row's keys in registers after ONE tcgen05.ld round trip (a one-thread-per-row version
+// spent its time in 13 dependent TMEM round trips per tile at 17 % occupancy), the quarter maxima meet in shared memory,
+// P = exp2(S*scale - max) is written IN PLACE over S (16-bit pairs; every quarter has read S before any writes), O = P V
+// with P as the TMEM A operand, the denominator riding along as the ones row of V^T like in the self-attention kernel.
+// ------------------------------------------------------------------------------------------
+struct XAttnParams {
+  int tq, tk, heads, d, kv_batch_div;
+  int q_tiles, total_tiles, tiles_per_cta;
+  int n_keys;                    // 160 or 80: N of Q K^T and K of P V
+  int qk_steps, n_o;
+  uint32_t idesc_s, idesc_o;
+  float scale_log2;
+  void* out;
+  long long out_pitch;
+};
+
+constexpr int XQST = 4;                       // Q ring depth
+constexpr uint32_t X_OFF_K = 0;               // 160 keys x 128 B
+constexpr uint32_t X_OFF_V = 20480;           // 3 chunks of 64 keys: 64 rows x 128 B each (n_o rows loaded)
+constexpr uint32_t X_VCHUNK = 8192;
+constexpr uint32_t X_OFF_Q = X_OFF_V + 3 * X_VCHUNK;
+constexpr uint32_t X_OFF_MAX = X_OFF_Q + XQST * 16384;      // float [2 buffers][4 quarters][128 rows]
+constexpr uint32_t X_OFF_BAR = X_OFF_MAX + 2 * 4 * 128 * 4;
+constexpr size_t X_SMEM = X_OFF_BAR + 256 + 1024;
+constexpr int X_THREADS = 16 * 32 + 4 * 32;     // 4 softmax warpgroups + one service warpgroup (TMA, Q K^T, P V, idle)
+
+// N (32 / 16 / 8) scores -> exp2 -> N/2 packed columns, stored at once so the scores' registers retire early
+template <bool BF16, int POLY, int N>
+__device__ __forceinline__ void xexp_store(const uint32_t* s, uint32_t dst, float2 sc2, float2 nref2) {
+  using E = Elem<BF16>;
+  constexpr int NP = N / 2 < 8 ? 8 : N / 2;
+  uint32_t pk[NP];
+#pragma unroll
+  for (int i = 0; i < N; i += 2) {
+    const float2 a = __ffma2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, nref2);
+    float2 e;
+    if ((POLY >> ((i >> 1) & 7)) & 1) e = poly_exp2_pair<BF16>(a);
+    else e = make_float2(fast_exp2(a.x), fast_exp2(a.y));
+    pk[i >> 1] = E::pack(e.x, e.y);
+  }
+  if constexpr (N == 32) tmem_st_32x32b_x16(dst, pk);
+  else if constexpr (N == 16) tmem_st_32x32b_x8(dst, pk);
+  else {
+    // 8 keys = 4 packed columns: padded to an x8 store with zeros (the extra columns belong to padding keys)
+#pragma unroll
+    for (int k = 4; k < 8; ++k) pk[k] = 0u;
+    tmem_st_32x32b_x8(dst, pk);
+  }
+}
+
+// one quarter row: NK keys starting at S column k_off; `valid` = how many of them are real keys (the rest is padding).
+// xm = this buffer's [4 quarters][128 rows] maxima.
+template <bool BF16, int POLY, int NK>
+__device__ __forceinline__ void xsoft_part(uint32_t t_s, int k_off, int valid, float sc, float* xm, int quarter, int row) {
+  uint32_t s[NK];
+  tmem_ld_cols<NK>(t_s + k_off, s);
+  tmem_ld_wait();
+  if (valid < NK) {
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+      if (k >= valid) s[k] = 0xff800000u;   // -inf
+  }
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NK; k += 4) {
+    mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s[k]), __uint_as_float(s[k + 1])));
+    mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s[k + 2]), __uint_as_float(s[k + 3])));
+  }
+  xm[quarter * 128 + row] = fmaxf(mx0, mx1);
+  asm volatile("bar.sync 1, 512;" ::: "memory");
+  const float ref = fmaxf(fmaxf(xm[row], xm[128 + row]), fmaxf(xm[256 + row], xm[384 + row])) * sc;
+  const float2 sc2 = make_float2(sc, sc), nref2 = make_float2(-ref, -ref);
+  constexpr int n32 = NK / 32, rem = NK % 32;
+#pragma unroll
+  for (int c = 0; c < n32; ++c) xexp_store<BF16, POLY, 32>(&s[32 * c], t_s + ((k_off + 32 * c) >> 1), sc2, nref2);
+  if constexpr (rem >= 16) xexp_store<BF16, POLY, 16>(&s[32 * n32], t_s + ((k_off + 32 * n32) >> 1), sc2, nref2);
+  static_assert(rem % 16 == 0, "quarter widths are multiples of 16");
+  tmem_st_wait();
+}
+
+template <bool BF16, int POLY, int K0, int K1, int K2, int K3>
+__global__ void __launch_bounds__(X_THREADS, 1)
+xattn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ XAttnParams p) {
+  using E = Elem<BF16>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + X_OFF_BAR);
+  uint64_t* kv_full = bars;                 // 1
+  uint64_t* kv_empty = kv_full + 1;         // 1
+  uint64_t* q_full = kv_empty + 1;          // XQST
+  uint64_t* q_empty = q_full + XQST;        // XQST
+  uint64_t* s_full = q_empty + XQST;        // 2
+  uint64_t* p_full = s_full + 2;            // 2
+  uint64_t* o_full = p_full + 2;            // 2
+  uint64_t* s_free = o_full + 2;            // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  float* xmax = reinterpret_cast<float*>(smem + X_OFF_MAX);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int t_begin = blockIdx.x * p.tiles_per_cta;
+  const int t_end = min(t_begin + p.tiles_per_cta, p.total_tiles);
+  const int n_tiles = t_end - t_begin;
+
+  auto kv_of = [&](int t) { const int bh = t / p.q_tiles; const int b = bh / p.heads; return (b / p.kv_batch_div) * p.heads + (bh - b * p.heads); };
+
+  if (threadIdx.x == 512) {
+    tma_prefetch_desc(&tm.q);
+    tma_prefetch_desc(&tm.k);
+    tma_prefetch_desc(&tm.vt);
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    for (int i = 0; i < XQST; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 512); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 512); }
+    fence_barrier_init();
+  }
+  if (warp == 17) tmem_alloc<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const int n_vchunks = (p.n_keys + 63) / 64;
+
+  if (warp >= 16) {
+  if (warp == 16) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && n_tiles > 0) {
+      const uint32_t kv_bytes = (uint32_t)p.n_keys * 128u + (uint32_t)n_vchunks * (uint32_t)p.n_o * 128u;
+      int seg = 0, prev_kv = -1;
+      for (int i = 0; i < n_tiles; ++i) {
+        const int t = t_begin + i;
+        const int kv = kv_of(t);
+        if (kv != prev_kv) {
+          if (seg > 0) mbar_wait(kv_empty, (seg - 1) & 1);      // every MMA that read the old K / V has completed
+          mbar_arrive_expect_tx(kv_full, kv_bytes);
+          tma_load_3d(smem + X_OFF_K, &tm.k, kv_full, 0, 0, kv);
+          for (int c = 0; c < n_vchunks; ++c) tma_load_3d(smem + X_OFF_V + c * X_VCHUNK, &tm.vt, kv_full, c * 64, 0, kv);
+          prev_kv = kv;
+          ++seg;
+        }
+        const int st = i % XQST;
+        mbar_wait(&q_empty[st], ((i / XQST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[st], 16384);
+        const int bh = t / p.q_tiles, qt = t - bh * p.q_tiles;
+        tma_load_3d(smem + X_OFF_Q + st * 16384, &tm.q, &q_full[st], 0, qt * 128, bh);
+      }
+    }
+  } else if (warp == 17) {
+    // ===================== Q K^T issuer (converged warp, one elected lane issues) =====================
+    const uint32_t k_base = smem_u32(smem + X_OFF_K);
+    const uint32_t v_base = smem_u32(smem + X_OFF_V);
+    const uint32_t q_base = smem_u32(smem + X_OFF_Q);
+    int seg = 0, prev_kv = -1;
+    for (int i = 0; i < n_tiles; ++i) {
+      const int kv = kv_of(t_begin + i);
+      if (kv != prev_kv) {
+        mbar_wait(kv_full, seg & 1);
+        // row `d` of V^T := 1  => O[:, d] = softmax denominator (same rounded P as the numerator)
+        if (lane < 8 * n_vchunks) {
+          const uint32_t one2 = BF16 ? 0x3F803F80u : 0x3C003C00u;
+          const uint32_t rowa = v_base + (lane >> 3) * X_VCHUNK + p.d * 128 + (lane & 7) * 16;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(rowa), "r"(one2) : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        prev_kv = kv;
+        ++seg;
+      }
+      const int st = i % XQST, b = i & 1;
+      mbar_wait(&q_full[st], (i / XQST) & 1);
+      // the S | P columns of this buffer are free as soon as the P V of tile i-2 has retired (its O is read later, from
+      // other columns): waiting for the epilogue instead left the whole Q K^T latency exposed in front of every softmax
+      if (i >= 2) mbar_wait(&o_full[b], ((i - 2) >> 1) & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint64_t a = umma_desc_k_sw128(q_base + st * 16384);
+        const uint64_t bd = umma_desc_k_sw128(k_base);
+        for (int k = 0; k < p.qk_steps; ++k) umma_f16_ss(tmem_base + b * 256, a + 2 * k, bd + 2 * k, p.idesc_s, k != 0);
+        umma_commit(&s_full[b]);
+        umma_commit(&q_empty[st]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 18) {
+    // ===================== P V issuer =====================
+    const uint32_t v_base = smem_u32(smem + X_OFF_V);
+    const int pv_steps = p.n_keys / 16;
+    for (int i = 0; i < n_tiles; ++i) {
+      const int b = i & 1;
+      mbar_wait(&p_full[b], (i >> 1) & 1);
+      mbar_wait(&s_free[b], ((i >> 1) & 1) ^ 1);      // the epilogue of tile i-2 has read this buffer's O columns
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t t_o = tmem_base + b * 256 + 192, t_p = tmem_base + b * 256;
+        for (int ks = 0; ks < pv_steps; ++ks) {
+          const uint64_t bd = umma_desc_k_sw128(v_base + (ks >> 2) * X_VCHUNK) + 2 * (ks & 3);
+          umma_f16_ts(t_o, t_p + ks * 8, bd, p.idesc_o, ks != 0);
+        }
+        umma_commit(&o_full[b]);
+        // last tile of a (text, head) segment: once these MMAs retire the K / V tiles may be replaced
+        if (i + 1 < n_tiles && kv_of(t_begin + i + 1) != kv_of(t_begin + i)) umma_commit(kv_empty);
+      }
+      __syncwarp();
+    }
+  }
+  } else {
+    // ===================== softmax: 16 warps, four threads per score row =====================
+    // Software-pipelined over the two TMEM buffers: softmax(i) then epilogue(i-1), so the P V of tile i runs under the
+    // epilogue of tile i-1 and the Q K^T of tile i+1 under the softmax of tile i.
+    const int quarter = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const float sc = p.scale_log2;
+    const int ng = (p.d + 15) >> 4;           // 16-column groups of O; group g is written by quarter g
+    for (int i = 0; i <= n_tiles; ++i) {
+      if (i < n_tiles) {
+        const int b = i & 1;
+        mbar_wait(&s_full[b], (i >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t t_s = t_lane + b * 256;
+        float* xm = xmax + b * 512;
+        switch (quarter) {
+          case 0: xsoft_part<BF16, POLY, K0>(t_s, 0, p.tk, sc, xm, 0, row); break;
+          case 1: xsoft_part<BF16, POLY, K1>(t_s, K0, p.tk - K0, sc, xm, 1, row); break;
+          case 2: xsoft_part<BF16, POLY, K2>(t_s, K0 + K1, p.tk - K0 - K1, sc, xm, 2, row); break;
+          default: xsoft_part<BF16, POLY, K3>(t_s, K0 + K1 + K2, p.tk - K0 - K1 - K2, sc, xm, 3, row); break;
+        }
+        tcgen05_fence_before();
+        mbar_arrive(&p_full[b]);
+      }
+      if (i > 0) {
+        // ---- epilogue of tile i-1: O[:, :d] / O[:, d] ----
+        const int j = i - 1, b = j & 1;
+        mbar_wait(&o_full[b], (j >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t t_o = t_lane + b * 256 + 192;
+        const int t = t_begin + j;
+        const int bh = t / p.q_tiles, qt = t - bh * p.q_tiles;
+        const int bi = bh / p.heads, head = bh - bi * p.heads;
+        const int tok = qt * 128 + row;
+        uint32_t lv[16], v[16];
+        tmem_ld_32x32b_x16(t_o + (p.d & ~15), lv);
+        if (quarter < ng) tmem_ld_32x32b_x16(t_o + 16 * quarter, v);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        mbar_arrive(&s_free[b]);              // this buffer's O is in registers: the P V of tile j+2 may overwrite it
+        if (quarter < ng && tok < p.tq) {
+          float l = 0.f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (k == (p.d & 15)) l = __uint_as_float(lv[k]);
+          const float inv_l = 1.0f / l;
+          typename E::T* out = reinterpret_cast<typename E::T*>(p.out) + (static_cast<long long>(bi) * p.tq + tok) * p.out_pitch + head * p.d;
+          uint32_t o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = E::pack(__uint_as_float(v[2 * k]) * inv_l, __uint_as_float(v[2 * k + 1]) * inv_l);
+          *reinterpret_cast<uint4*>(out + 16 * quarter) = make_uint4(o[0], o[1], o[2], o[3]);
+          if (16 * quarter + 8 < p.d) *reinterpret_cast<uint4*>(out + 16 * quarter + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <bool BF16, int POLY, int K0, int K1, int K2, int K3>
+static int launch_xattn(const AttnTmaps& tm, const XAttnParams& p, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_kernel<BF16, POLY, K0, K1, K2, K3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X_SMEM);
+    if (e != cudaSuccess) {
+      set_last_error("cross-attention: cudaFuncSetAttribute(%zu B) failed: %s", X_SMEM, cudaGetErrorString(e));
+      return TCL_ERR_CUDA;
+    }
+    configured = true;
+  }
+  xattn_kernel<BF16, POLY, K0, K1, K2, K3><<<grid, X_THREADS, X_SMEM, stream>>>(tm, p);
+  TCL_CHECK_LAUNCH("tcl_attention(cross)");
+  return TCL_OK;
+}
+
 template <int NQ, int DPAD, int KST, int VST, bool BF16, int POLY, bool PACKED, bool STALE, int MINB = 1, int REGS = 0>
 static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, int bh, cudaStream_t stream) {
   constexpr size_t smem = (size_t)NQ * 128 * DPAD * 2 + (size_t)KST * 128 * DPAD * 2 + (size_t)VST * 2 * DPAD * 128 + 1024 + 256;
@@ -580,6 +876,33 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
     // short key sequences (cross-attention on the 77 / 154 text tokens): the per-CTA latency chain (TMEM alloc, Q / K / V
     // loads, two serial tiles, epilogue) dominates, so run one Q tile per CTA and two CTAs per SM (256 TMEM columns,
     // 85 KB of shared memory each) to overlap the chains of neighbouring tiles
+    const int n_keys16 = (a->tk + 15) / 16 * 16;
+    if ((n_keys16 == 160 || n_keys16 == 80) && g_attn_variant != 0) {
+      // persistent cross-attention (L = 154 / 77): K / V^T resident per (text, head), Q streamed, one TMEM allocation per CTA
+      XAttnParams x;
+      x.tq = a->tq; x.tk = a->tk; x.heads = a->heads; x.d = a->d; x.kv_batch_div = a->kv_batch_div;
+      x.q_tiles = q_tiles; x.total_tiles = q_tiles * bh;
+      int sms = 148;
+      { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+      const int grid = x.total_tiles < sms ? x.total_tiles : sms;
+      x.tiles_per_cta = (x.total_tiles + grid - 1) / grid;
+      x.n_keys = n_keys16;
+      x.qk_steps = p.qk_steps; x.n_o = p.n_o;
+      x.idesc_s = umma_idesc_f16(bf16, 128, (uint32_t)x.n_keys); x.idesc_o = p.idesc_o;
+      x.scale_log2 = p.scale_log2; x.out = p.out; x.out_pitch = p.out_pitch;
+      AttnTmaps xm = tm;
+      {
+        const uint64_t dims[3] = {(uint64_t)a->d_pad, (uint64_t)a->tk, (uint64_t)kv_bh};
+        const uint64_t str[2] = {(uint64_t)a->d_pad * 2, (uint64_t)a->tk_pitch * a->d_pad * 2};
+        const uint32_t box[3] = {64, (uint32_t)x.n_keys, 1}, es[3] = {1, 1, 1};
+        int rc = make_tmap(&xm.k, a->k, bf16, 3, dims, str, box, es, 128);
+        if (rc) return rc;
+      }
+      const int grid_used = (x.total_tiles + x.tiles_per_cta - 1) / x.tiles_per_cta;
+      if (x.n_keys == 160)
+        return bf16 ? launch_xattn<true, 0x11, 48, 32, 48, 32>(xm, x, grid_used, stream) : launch_xattn<false, 0x11, 48, 32, 48, 32>(xm, x, grid_used, stream);
+      return bf16 ? launch_xattn<true, 0x11, 32, 16, 16, 16>(xm, x, grid_used, stream) : launch_xattn<false, 0x11, 32, 16, 16, 16>(xm, x, grid_used, stream);
+    }
     if (a->tk <= 256) {
       return bf16 ? launch_attn<1, 64, 2, 2, true, 0x11, true, false, 2>(tm, p, q_tiles, bh, stream)
                   : launch_attn<1, 64, 2, 2, false, 0x00, true, false, 2>(tm, p, q_tiles, bh, stream);

@@ -310,6 +310,36 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// N consecutive columns (N a multiple of 8) as the largest x32 / x16 / x8 pieces, issued back to back (one wait afterwards)
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[N]) {
+  static_assert(N % 8 == 0, "tmem_ld_cols");
+  constexpr int n32 = N / 32, rem = N % 32;
+#pragma unroll
+  for (int i = 0; i < n32; ++i) tmem_ld_32x32b_x32(taddr + 32 * i, *reinterpret_cast<uint32_t (*)[32]>(&r[32 * i]));
+  if constexpr (rem >= 16) tmem_ld_32x32b_x16(taddr + 32 * n32, *reinterpret_cast<uint32_t (*)[16]>(&r[32 * n32]));
+  if constexpr (rem % 16 == 8) tmem_ld_32x32b_x8(taddr + N - 8, *reinterpret_cast<uint32_t (*)[8]>(&r[N - 8]));
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&r)[N]) {
+  static_assert(N % 8 == 0, "tmem_st_cols");
+  constexpr int n32 = N / 32, rem = N % 32;
+#pragma unroll
+  for (int i = 0; i < n32; ++i) tmem_st_32x32b_x32(taddr + 32 * i, *reinterpret_cast<const uint32_t (*)[32]>(&r[32 * i]));
+  if constexpr (rem >= 16) tmem_st_32x32b_x16(taddr + 32 * n32, *reinterpret_cast<const uint32_t (*)[16]>(&r[32 * n32]));
+  if constexpr (rem % 16 == 8) tmem_st_32x32b_x8(taddr + N - 8, *reinterpret_cast<const uint32_t (*)[8]>(&r[N - 8]));
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
