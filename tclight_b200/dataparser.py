@@ -141,7 +141,8 @@ class VideoDataParser:
 
     def _one_flow(self, idx, gts, frame_ids, is_future, path, save):
         fname = os.path.join(path, f"{frame_ids[idx]:04d}.pt")
-        if os.path.exists(fname):
+        # video_dataparser.py:115: a cached flow is only trusted when the cache holds exactly this frame selection
+        if os.path.exists(fname) and len(os.listdir(path)) == len(frame_ids):
             return torch.load(fname, map_location="cpu")
         zero_idx = gts.shape[0] - 1 if is_future else 0
         src = gts[idx:idx + 1]

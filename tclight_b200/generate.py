@@ -343,7 +343,7 @@ class Generator(VidToMeGenerator):
 
     @torch.no_grad()
     def relight(self, frames, prompt_embeds, prompt_embeds_t, future_flows=None, past_flows=None, flow_alpha=0.5,
-                rgb_threshold=0.01):
+                rgb_threshold=0.01, prepared=None):
         """The device-resident core of ``Generator.__call__`` (generate.py:560-604) for one prompt, with everything
         outside SURVEY §8 (CLIP text encoding, video decoding, the optical-flow network) supplied by the caller:
 
@@ -351,7 +351,9 @@ class Generator(VidToMeGenerator):
             future_flows / past_flows [N,2,H,W] (needed when post_opt.apply_opt)
 
         VAE-encode the frames as the IC-Light condition -> multi-axis denoising -> VAE decode -> soft masks, flow ids,
-        unique inverse -> exposure alignment -> unique-video-tensor optimisation.  Returns (frames_out, info)."""
+        unique inverse -> exposure alignment -> unique-video-tensor optimisation.  Returns (frames_out, info).
+        ``prepared`` = the dict of ``prepare_relight`` when several prompts share one clip (the reference's prepare_data
+        draws the initial noise and builds masks / unq_inv once, before its prompt loop)."""
         from . import flow_utils
         from .postopt import OptDataset
 
@@ -359,16 +361,16 @@ class Generator(VidToMeGenerator):
         self.scheduler.set_timesteps(self.n_timesteps, device=self.device)
         if self.rng is None:
             self.rng = [torch.Generator(device=self.device).manual_seed(int(self.seed))] * N
-        concat_conds = self.encode_imgs_batch(frames)
-        init_noise = self.prepare_latents(N, concat_conds.shape[2], concat_conds.shape[3])
+        if prepared is None:
+            prepared = self.prepare_relight(frames, future_flows, past_flows, flow_alpha, rgb_threshold)
+        concat_conds, init_noise = prepared["concat_conds"], prepared["init_noise"]
         clean_latent = self.ddim_sample(init_noise, prompt_embeds, prompt_embeds_t, concat_conds)
         clean_frames = self.decode_latents_batch(clean_latent)
         info = {"latent": clean_latent}
         if self.apply_opt:
             if future_flows is None or past_flows is None:
                 raise TclError("relight: post_opt.apply_opt needs future_flows and past_flows")
-            masks, unq_inv = flow_utils.build_unq_inv(frames.float(), future_flows.float(), past_flows.float(), alpha=flow_alpha,
-                                                      rgb_threshold=rgb_threshold)
+            masks, unq_inv = prepared["masks"], prepared["unq_inv"]
             if self.data_parser is None:
                 self.data_parser = type("DataParser", (), {})()
             self.data_parser.unq_inv = unq_inv
@@ -377,6 +379,24 @@ class Generator(VidToMeGenerator):
             clean_frames, info["loss_unique_tensor"] = self.unique_tensor_optimization()
             info["unq_inv"], info["mask_bwds"] = unq_inv, masks
         return clean_frames, info
+
+    @torch.no_grad()
+    def prepare_relight(self, frames, future_flows=None, past_flows=None, flow_alpha=0.5, rgb_threshold=0.01, flow_model="memflow"):
+        """Per-clip inputs shared by every prompt (generate.py prepare_data): condition latents, ONE draw of the initial
+        noise, and - when the optimiser runs - soft masks and the unique-tensor inverse."""
+        from . import flow_utils
+
+        N = frames.shape[0]
+        if self.rng is None:
+            self.rng = [torch.Generator(device=self.device).manual_seed(int(self.seed))] * N
+        concat_conds = self.encode_imgs_batch(frames)
+        out = {"concat_conds": concat_conds, "init_noise": self.prepare_latents(N, concat_conds.shape[2], concat_conds.shape[3])}
+        if self.apply_opt:
+            if future_flows is None or past_flows is None:
+                raise TclError("relight: post_opt.apply_opt needs future_flows and past_flows")
+            out["masks"], out["unq_inv"] = flow_utils.build_unq_inv(frames.float(), future_flows.float(), past_flows.float(),
+                                                                    alpha=flow_alpha, rgb_threshold=rgb_threshold, flow_model=flow_model)
+        return out
 
     def __call__(self, latent_path, output_path, frame_ids):
         """generate.py:560-630 with the B200 path.  Needs ``pipe.data_parser`` exposing ``load_video(frame_ids=...)`` and
@@ -394,11 +414,13 @@ class Generator(VidToMeGenerator):
         if self.apply_opt:
             flows, past, _ = dp.load_flow(frame_ids, True, True, frames)
         results = {}
+        prepared = self.prepare_relight(frames.to(self.device), flows, past, flow_alpha=getattr(dp, "alpha", 0.5),
+                                        flow_model=getattr(dp, "flow_model", "memflow"))
         for name, prompt in self.prompt.items():
             c, u = self.encode_prompt_pair(prompt, self.negative_prompt)
             ct, ut = self.encode_prompt_pair(self.prompt_t, self.negative_prompt_t)
             out, info = self.relight(frames.to(self.device), torch.cat([u, c]), torch.cat([ut, ct]), flows, past,
-                                     flow_alpha=getattr(dp, "alpha", 0.5))
+                                     flow_alpha=getattr(dp, "alpha", 0.5), prepared=prepared)
             results[name] = (out, info)
             if output_path:
                 # generate.py:611-630: one folder per prompt with the relit video, the input video and the loss curves

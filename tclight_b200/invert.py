@@ -162,6 +162,9 @@ class Inverter(nn.Module):
     @torch.no_grad()
     def __call__(self, save_path, frame_ids=None):
         self.scheduler.set_timesteps(self.steps)
+        # get_latents_dir (utils/VidToMe/utils.py:304-309, invert.py:276): one sub-directory per model key
+        model_key = getattr(self, "model_key", None)
+        save_path = os.path.join(save_path, model_key.split("/")[-1] if model_key is not None else "default")
         os.makedirs(save_path, exist_ok=True)
         if self.check_latent_exists(save_path) and not self.force:
             print(f"[INFO] inverted latents exist at: {save_path}. Skip inversion! Set 'inversion.force: True' to invert again.")

@@ -48,6 +48,8 @@ class OptDataset(torch.utils.data.Dataset):
         if dtype != torch.float32:
             raise TclError("the optimiser kernels are fp32 (as the reference's OptDataset default)")
         self.edited_images = edited_images.to(dtype=dtype, device=device).contiguous()
+        if self.edited_images.data_ptr() == edited_images.data_ptr():
+            self.edited_images = self.edited_images.clone()      # exposure_align bakes in place: never into the caller's tensor
         self.past_flows = past_flows.to(dtype=dtype, device=device).contiguous() if past_flows is not None else None
         self.mask_bwd = mask_bwd.to(device=device, dtype=dtype).contiguous() if mask_bwd is not None else None
         self.device, self.dtype = device, dtype

@@ -74,3 +74,49 @@ def test_sharded_passes_equal_single_process():
         for w in (1, 2, 4, 8):
             edges = [_make(r, w)._my_range(n) for r in range(w)]
             assert edges[0][0] == 0 and edges[-1][1] == n and all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+
+
+# ---- data-parallel optimiser host logic (tclight_b200/postopt.py): batch slicing and the CPU-RNG hand-over ----
+def test_shard_batch_partitions_sorted_batch():
+    from tclight_b200.postopt import shard_batch
+
+    idxs = [17, 3, 250, 0, 42, 299, 8, 120, 64, 5, 199, 77]
+    for world in (1, 2, 3, 8):
+        parts = [shard_batch(idxs, r, world) for r in range(world)]
+        got = [i for p, _, _ in parts for i in p]
+        assert got == sorted(idxs)                                  # contiguous slices of the sorted batch, nothing lost
+        assert all(n == len(idxs) and nv == len(idxs) - 1 for _, n, nv in parts)     # global normalisers on every rank
+        sizes = [len(p) for p, _, _ in parts]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _rng_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tclight_b200.postopt import _sync_cpu_rng, batch_iterator
+
+    torch.manual_seed(5)
+    if rank > 0:
+        torch.randperm(2 + rank)            # the sharded denoising passes leave the ranks' CPU RNGs in different states
+    _sync_cpu_rng(torch.device("cpu"))
+    draws = [[int(i) for i in b] for b in batch_iterator(7, 4)]
+    q.put((rank, draws))
+    dist.destroy_process_group()
+
+
+def test_dp_ranks_draw_identical_batches_after_rng_sync():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_rng_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    torch.manual_seed(5)
+    from tclight_b200.postopt import batch_iterator
+    want = [[int(i) for i in b] for b in batch_iterator(7, 4)]
+    assert out[0] == out[1] == want         # = what rank 0 / a single-GPU run draws
