@@ -43,6 +43,7 @@ def parse():
     p.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-ref-on-b200", action="store_true")
+    p.add_argument("--no-aux", action="store_true")
     p.add_argument("--stage2-iters", type=int, default=20)
     return p.parse_args()
 
@@ -512,6 +513,12 @@ def run_b200(args):
             line["cpu_baseline"] = cpu_baseline(args, step_tflop=line["path_tflop_per_step_all_ranks"] or None)
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
+    if rank == 0 and not args.no_aux:
+        try:
+            line["aux"] = aux_legs(dev, adt, H, W)
+        except Exception as ex:  # noqa: BLE001
+            line["aux"] = {"error": str(ex)[:200]}
+        torch.cuda.empty_cache()
     if args.stage2_iters > 0:
         from tclight_b200 import postopt
         line["stage2"], line["stage1"] = postopt.bench_postopt(dev, N, H, W, iters=args.stage2_iters, rank=rank, world=world,
@@ -526,6 +533,65 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def aux_legs(dev, adt, H, W):
+    """The callers either side of the denoising path at the bench resolution (BASELINE config 5 names them):
+    VAE encode / decode (frames/s, batch 4) and one DDIM-inversion step of `Inverter` (un-patched UNet, no CFG, batch 8,
+    invert.py:151-173).  Per-GPU rates on seeded random SD-1.5-shaped weights; frames shard trivially across ranks."""
+    import types
+
+    import torch
+    from tclight_b200.invert import Inverter
+    from tclight_b200.scheduler import DDIMSchedulerB200
+    from tclight_b200.unet import UNetB200
+    from tclight_b200.vae import AutoencoderKLB200
+    from tclight_b200.weights import random_state_dict, random_vae_state_dict
+
+    def ms_of(fn, warm=1, k=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(k):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / k
+
+    out = {}
+    h, w = H // 8, W // 8
+    vae = AutoencoderKLB200(random_vae_state_dict(seed=0), device=dev, dtype=adt)
+    lat = (0.18215 * torch.randn(4, 4, h, w, device=dev)).to(adt)
+    img = torch.rand(4, 3, H, W, device=dev)
+    out["vae_decode_frames_per_sec"] = 4e3 / ms_of(lambda: vae.decode_latents(lat))
+    out["vae_encode_frames_per_sec"] = 4e3 / ms_of(lambda: vae.encode_imgs(img))
+    del vae, lat, img
+    torch.cuda.empty_cache()
+
+    class D(dict):
+        __getattr__ = dict.__getitem__
+
+    fp = "fp16" if adt == torch.float16 else "bf16"
+    cfg = types.SimpleNamespace(device="cuda", sd_version="1.5", model_key=None, float_precision=fp, height=H, width=W, work_dir=".",
+                                inversion=D(float_precision=fp, control="none", control_scale=1.0, save_steps=50, steps=50, prompt="",
+                                            recon=False, save_intermediate=False, use_blip=False, batch_size=8, force=True, n_frames=None))
+    unet = UNetB200(random_state_dict(seed=0, in_channels=4), device=dev, dtype=adt)
+    inv = Inverter(types.SimpleNamespace(unet=unet), DDIMSchedulerB200(), cfg)
+    x = torch.randn(8, 4, h, w, device=dev).to(inv.dtype if hasattr(inv, "dtype") else adt)
+    conds = torch.randn(8, 77, 768, device=dev).to(adt)
+    ts = list(reversed(inv.scheduler.timesteps))
+
+    def one():
+        eps = inv._all_noise(x, conds, ts[3])
+        inv.pred_next_x(x, eps, ts[3], 3, inversion=True)
+
+    ms = ms_of(one)
+    out["inversion_frame_steps_per_sec"] = 8e3 / ms
+    out["inversion_note"] = ("Inverter: one DDIM-inversion step of 8 frames (un-patched SD-1.5 UNet forward, L=77, no CFG, + tcl_ddim_next); "
+                             "a clip needs frames x 50 such frame-steps")
+    return out
 
 
 def stage2_convergence_vs_oracle(dev):
