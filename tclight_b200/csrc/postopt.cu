@@ -655,7 +655,8 @@ __global__ void __launch_bounds__(256, 4)
 level0_uvt_kernel(L0Params q, Shards sh, float inv_nseg) {
   __shared__ float red[3][8];
   const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);     // warp-uniform for the compiler: the chunk loop is convergent
   const int b = blockIdx.y;
   const int fr = q.bt.idx[b];
   const bool valid = fr > 0;
@@ -734,40 +735,44 @@ level0_uvt_kernel(L0Params q, Shards sh, float inv_nseg) {
       if (s[0] == 0.f && s[1] == 0.f && s[2] == 0.f) left = 0u;
       const bool main_on = real && tf != 0u;
       const int o0 = bc.y0 * q.W + bc.x0;
+      // all 36 shuffles first, in straight-line code (the reductions below diverge)
+      float out[4][3];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float wy = bc.cy[j];
-        const unsigned fl = (tf >> (3 * j)) & 7u;
-        int id = 0;
-        if (main_on && fl) id = __ldg(ids_pre + o0 + j * q.W);
-        float v[4][3];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float wgt = bc.cx[i] * wy;
+        for (int c = 0; c < 3; ++c) out[j][c] = s[c] * (bc.cx[0] * wy);
 #pragma unroll
-          for (int c = 0; c < 3; ++c) v[i][c] = s[c] * wgt;
+        for (int k = 1; k <= 3; ++k) {
+          const float wgt = bc.cx[k] * wy;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) out[j][c] = fmaf(__shfl_up_sync(FULL, s[c] * wgt, k), accf[k], out[j][c]);
         }
-        float out[3] = {v[0][0], v[0][1], v[0][2]};
+      }
+      if (main_on) {
 #pragma unroll
-        for (int k = 1; k <= 3; ++k)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) out[c] = fmaf(__shfl_up_sync(FULL, v[k][c], k), accf[k], out[c]);
-        if (main_on && fl) sink(id, fl, out[0], out[1], out[2]);
-        if (left) {                                  // rare: broken chain / image border
+        for (int j = 0; j < 4; ++j) {
+          const unsigned fl = (tf >> (3 * j)) & 7u;
+          if (fl) sink(__ldg(ids_pre + o0 + j * q.W), fl, out[j][0], out[j][1], out[j][2]);
+        }
+      }
+      if (left) {                                    // rare: broken chain / image border
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
           const int yy = bc.y0 + j;
-          if (yy >= 0 && yy < q.H) {
-#pragma unroll
-            for (int i = 1; i <= 3; ++i) {
-              const int xx = bc.x0 + i;
-              if (!((left >> i) & 1u) || xx < 0 || xx >= q.W) continue;
-              const unsigned fli = __float_as_uint(__ldg(Xp + yy * q.W + xx).w) & 7u;
-              if (fli) sink(ids_pre[yy * q.W + xx], fli, v[i][0], v[i][1], v[i][2]);
-            }
+          if (yy < 0 || yy >= q.H) continue;
+#pragma unroll 1
+          for (int i = 1; i <= 3; ++i) {
+            const int xx = bc.x0 + i;
+            if (!((left >> i) & 1u) || xx < 0 || xx >= q.W) continue;
+            const unsigned fli = __float_as_uint(__ldg(Xp + yy * q.W + xx).w) & 7u;
+            const float wgt = bc.cx[i] * bc.cy[j];
+            if (fli) sink(ids_pre[yy * q.W + xx], fli, s[0] * wgt, s[1] * wgt, s[2] * wgt);
           }
         }
       }
     }
-    if (!real) continue;
+    if (real) {
     // ---- total variation ----
     if (q.k_tvh != 0.f) {
       const float xi[3] = {own.x, own.y, own.z};
@@ -806,6 +811,7 @@ level0_uvt_kernel(L0Params q, Shards sh, float inv_nseg) {
     // ---- sink ----
     const unsigned fl = __float_as_uint(own.w) & 7u;
     if (fl) sink(ids_cur[p], fl, g[0], g[1], g[2]);
+    }
   }
   acc_flow = warp_sum(acc_flow); acc_tvh = warp_sum(acc_tvh); acc_tvw = warp_sum(acc_tvw);
   if (lane == 0) { red[0][warp] = acc_flow; red[1][warp] = acc_tvh; red[2][warp] = acc_tvw; }
