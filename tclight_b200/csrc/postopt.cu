@@ -735,39 +735,35 @@ level0_uvt_kernel(L0Params q, Shards sh, float inv_nseg) {
       if (s[0] == 0.f && s[1] == 0.f && s[2] == 0.f) left = 0u;
       const bool main_on = real && tf != 0u;
       const int o0 = bc.y0 * q.W + bc.x0;
-      // all 36 shuffles first, in straight-line code (the reductions below diverge)
-      float out[4][3];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float wy = bc.cy[j];
+        const unsigned fl = (tf >> (3 * j)) & 7u;
+        int id = 0;
+        if (main_on && fl) id = __ldg(ids_pre + o0 + j * q.W);
+        float v[4][3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) out[j][c] = s[c] * (bc.cx[0] * wy);
+        for (int i = 0; i < 4; ++i) {
+          const float wgt = bc.cx[i] * wy;
 #pragma unroll
-        for (int k = 1; k <= 3; ++k) {
-          const float wgt = bc.cx[k] * wy;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) out[j][c] = fmaf(__shfl_up_sync(FULL, s[c] * wgt, k), accf[k], out[j][c]);
+          for (int c = 0; c < 3; ++c) v[i][c] = s[c] * wgt;
         }
-      }
-      if (main_on) {
+        float out[3] = {v[0][0], v[0][1], v[0][2]};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const unsigned fl = (tf >> (3 * j)) & 7u;
-          if (fl) sink(__ldg(ids_pre + o0 + j * q.W), fl, out[j][0], out[j][1], out[j][2]);
-        }
-      }
-      if (left) {                                    // rare: broken chain / image border
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
+        for (int k = 1; k <= 3; ++k)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) out[c] = fmaf(__shfl_up_sync(FULL, v[k][c], k), accf[k], out[c]);
+        if (main_on && fl) sink(id, fl, out[0], out[1], out[2]);
+        if (left) {                                  // rare: broken chain / image border
           const int yy = bc.y0 + j;
-          if (yy < 0 || yy >= q.H) continue;
-#pragma unroll 1
-          for (int i = 1; i <= 3; ++i) {
-            const int xx = bc.x0 + i;
-            if (!((left >> i) & 1u) || xx < 0 || xx >= q.W) continue;
-            const unsigned fli = __float_as_uint(__ldg(Xp + yy * q.W + xx).w) & 7u;
-            const float wgt = bc.cx[i] * bc.cy[j];
-            if (fli) sink(ids_pre[yy * q.W + xx], fli, s[0] * wgt, s[1] * wgt, s[2] * wgt);
+          if (yy >= 0 && yy < q.H) {
+#pragma unroll
+            for (int i = 1; i <= 3; ++i) {
+              const int xx = bc.x0 + i;
+              if (!((left >> i) & 1u) || xx < 0 || xx >= q.W) continue;
+              const unsigned fli = __float_as_uint(__ldg(Xp + yy * q.W + xx).w) & 7u;
+              if (fli) sink(ids_pre[yy * q.W + xx], fli, v[i][0], v[i][1], v[i][2]);
+            }
           }
         }
       }
