@@ -114,13 +114,6 @@ typedef struct {
 } tcl_attn_desc;
 
 int tcl_attention(const tcl_attn_desc* desc, tcl_stream_t stream);
-/* tuning hooks (tools/bench_attn_variants.py): kernel variant used by tcl_attention (-1 = shipped configuration; see the
- * dispatch in csrc/attn.cu) and trimming of the MMA shapes to the live head-dim columns; return the previous value */
-int tcl_debug_attention_variant(int variant);
-int tcl_debug_attention_trim(int on);
-/* debug hook, active only in -DTCL_ATTN_TRACE builds: device int64[192] event log (see attn.cu) */
-void tcl_debug_attention_trace(long long* buf);
-
 /* ---- normalisation / staging (HBM-bound) --------------------------------------------------
  * GroupNorm(+SiLU) of diffusers ResnetBlock2D / Transformer2DModel / conv_norm_out over NHWC,
  * reading the channel concat [x1 | x2] of an up-block skip connection on the fly (x2 may be

@@ -270,10 +270,22 @@ lib.tcl_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.
                               C.c_float, C.c_int, C.c_void_p]
 lib.tcl_adam_step.restype = C.c_int
 
-lib.tcl_debug_attention_variant.argtypes = [C.c_int]
-lib.tcl_debug_attention_variant.restype = C.c_int
-lib.tcl_debug_attention_trim.argtypes = [C.c_int]
-lib.tcl_debug_attention_trim.restype = C.c_int
+
+
+def load_tuning_lib():
+    """libtclight_tuning.so: the attention kernel built with its tuning variants and debug hooks (include/tclight_tuning.h).
+    Test / tool infrastructure only; returns None when it has not been built."""
+    path = os.path.join(_HERE, "libtclight_tuning.so")
+    if not os.path.exists(path):
+        return None
+    t = C.CDLL(path)
+    t.tcl_attention.argtypes, t.tcl_attention.restype = lib.tcl_attention.argtypes, C.c_int
+    t.tcl_last_error.restype = C.c_char_p
+    t.tcl_debug_attention_variant.argtypes, t.tcl_debug_attention_variant.restype = [C.c_int], C.c_int
+    t.tcl_debug_attention_trim.argtypes, t.tcl_debug_attention_trim.restype = [C.c_int], C.c_int
+    t.tcl_debug_attention_trace.argtypes, t.tcl_debug_attention_trace.restype = [C.c_void_p], None
+    return t
+
 lib.tcl_ddim_next.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float,
                               C.c_float, C.c_void_p]
 lib.tcl_ddim_next.restype = C.c_int

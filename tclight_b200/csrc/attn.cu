@@ -821,9 +821,18 @@ static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, in
 
 using namespace tcl;
 
+// The product library ships ONE configuration per head-dim class.  The alternatives the sweep in
+// profiles/r02_attention_variants.txt compared (scalar vs packed arithmetic, FMA-pipe exp2 share, stale reference, untrimmed MMA
+// shapes) are compiled only into libtclight_tuning.so (-DTCL_ATTN_TUNING, `make tuning`; include/tclight_tuning.h).
+#ifdef TCL_ATTN_TUNING
 static int g_attn_variant = -1;  // -1 = shipped configuration; >= 0 selects a tuning variant (tools/bench_attn_variants.py)
 static int g_attn_trim = 1;      // 0 = issue the full padded MMA shapes (tuning reference)
 static long long* g_attn_trace = nullptr;
+#else
+constexpr int g_attn_variant = -1;
+constexpr int g_attn_trim = 1;
+constexpr long long* g_attn_trace = nullptr;
+#endif
 
 extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
   TCL_CHECK_ARG(a != nullptr, "tcl_attention: null descriptor");
@@ -909,24 +918,31 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
     }
     // long key sequences (merged self-attention): two Q tiles per CTA, packed-pair arithmetic, 2 of every 8 pairs of
     // exponentials on the FMA pipe, 200 registers per softmax thread (measured sweep: profiles/r02_attention_variants.txt)
+#ifdef TCL_ATTN_TUNING
     if (!bf16) {
       switch (var) {
         case 0: return launch_attn<2, 64, 4, 3, false, 0x00, false, false>(tm, p, q_tiles, bh, stream);
         case 8: return launch_attn<2, 64, 4, 3, false, 0x11, true, true, 1, 200>(tm, p, q_tiles, bh, stream);
-        default: return launch_attn<2, 64, 4, 3, false, 0x11, true, false, 1, 200>(tm, p, q_tiles, bh, stream);
+        default: break;
+      }
+    } else {
+      switch (var) {
+        case 0: return launch_attn<2, 64, 4, 3, true, 0x03, false, false>(tm, p, q_tiles, bh, stream);
+        case 5: return launch_attn<2, 64, 4, 3, true, 0x49, true, false, 1, 200>(tm, p, q_tiles, bh, stream);
+        case 8: return launch_attn<2, 64, 4, 3, true, 0x11, true, true, 1, 200>(tm, p, q_tiles, bh, stream);
+        default: break;
       }
     }
-    switch (var) {
-      case 0: return launch_attn<2, 64, 4, 3, true, 0x03, false, false>(tm, p, q_tiles, bh, stream);
-      case 5: return launch_attn<2, 64, 4, 3, true, 0x49, true, false, 1, 200>(tm, p, q_tiles, bh, stream);
-      case 8: return launch_attn<2, 64, 4, 3, true, 0x11, true, true, 1, 200>(tm, p, q_tiles, bh, stream);
-      default: return launch_attn<2, 64, 4, 3, true, 0x11, true, false, 1, 200>(tm, p, q_tiles, bh, stream);
-    }
+#endif
+    return bf16 ? launch_attn<2, 64, 4, 3, true, 0x11, true, false, 1, 200>(tm, p, q_tiles, bh, stream)
+                : launch_attn<2, 64, 4, 3, false, 0x11, true, false, 1, 200>(tm, p, q_tiles, bh, stream);
   } else if (a->d_pad == 128) {
     // one Q tile per CTA (TMEM: 128 S + 128 O + 64 P): registers are plentiful, the stale-reference softmax wins (+8 %)
+#ifdef TCL_ATTN_TUNING
     if (var == 0)
       return bf16 ? launch_attn<1, 128, 3, 2, true, 0, false, false>(tm, p, q_tiles, bh, stream)
                   : launch_attn<1, 128, 3, 2, false, 0, false, false>(tm, p, q_tiles, bh, stream);
+#endif
     return bf16 ? launch_attn<1, 128, 3, 2, true, 0x11, true, true>(tm, p, q_tiles, bh, stream)
                 : launch_attn<1, 128, 3, 2, false, 0x00, true, true>(tm, p, q_tiles, bh, stream);
   } else {
@@ -935,6 +951,7 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
   }
 }
 
+#ifdef TCL_ATTN_TUNING
 // Tuning hooks (tools/bench_attn_variants.py): kernel variant (-1 = shipped) and MMA-shape trimming; return the previous value.
 extern "C" int tcl_debug_attention_variant(int v) {
   const int old = g_attn_variant;
@@ -951,3 +968,4 @@ extern "C" int tcl_debug_attention_trim(int on) {
 // CTA (0,0) for KV tiles 64..71: role 0/1 = softmax warpgroup q {wait S, got S, loaded S, exp done, got P-empty, P stored},
 // role 2 = MMA thread {q0: wait S-empty, got it, wait P-full, got it; q1: the same}.
 extern "C" void tcl_debug_attention_trace(long long* buf) { g_attn_trace = buf; }
+#endif

@@ -5,6 +5,30 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def _variant(variant):
+    """variant -1 = the product library; the tuning variants live in libtclight_tuning.so (include/tclight_tuning.h), which
+    is swapped in for ops.attention while the block runs."""
+    from tclight_b200 import _lib, ops
+
+    if variant == -1:
+        yield
+        return
+    t = _lib.load_tuning_lib()
+    if t is None:
+        pytest.skip("libtclight_tuning.so not built (make -C tclight_b200/csrc tuning)")
+    old_lib, old_var = ops.lib, t.tcl_debug_attention_variant(variant)
+    ops.lib = t
+    try:
+        yield
+    finally:
+        ops.lib = old_lib
+        t.tcl_debug_attention_variant(old_var)
 TOL = {torch.float16: 3e-3, torch.bfloat16: 1.5e-2}
 
 
@@ -50,10 +74,8 @@ def test_attention_variants(cuda, dtype, variant):
     """Every tuning variant of the kernel (scalar / packed-pair arithmetic, FMA-pipe exp2 share, stale reference) is held
     to the same tolerance as the shipped one."""
     from tclight_b200 import ops
-    from tclight_b200._lib import lib
 
-    old = lib.tcl_debug_attention_variant(variant)
-    try:
+    with _variant(variant):
         for (B, H, Tq, Tk, d, div) in [(2, 8, 1024, 1024, 40, 1), (2, 8, 300, 300, 40, 1), (1, 8, 257, 640, 80, 1),
                                        (2, 8, 130, 130, 160, 1), (4, 8, 200, 154, 40, 2)]:
             torch.manual_seed(0)
@@ -68,8 +90,6 @@ def test_attention_variants(cuda, dtype, variant):
             ref = torch.einsum("bhqk,bhkd->bhqd", s.softmax(-1), vv).permute(0, 2, 1, 3).reshape(B, Tq, H * d)
             err = ((out.float() - ref).norm() / ref.norm()).item()
             assert err < TOL[dtype], (variant, d, err)
-    finally:
-        lib.tcl_debug_attention_variant(old)
 
 
 @pytest.mark.parametrize("variant", [-1, 0, 8])
@@ -80,10 +100,8 @@ def test_attention_row_max_jumps_between_tiles(cuda, dtype, variant, boost):
     the lazy rescale, the deferred rescale of the stale-reference variants and their overflow slow path (the scores are
     re-read from TMEM and the tile is redone against the new reference)."""
     from tclight_b200 import ops
-    from tclight_b200._lib import lib
 
-    old = lib.tcl_debug_attention_variant(variant)
-    try:
+    with _variant(variant):
         B, H, Tq, Tk, d = 1, 8, 300, 700, 40
         torch.manual_seed(3)
         d_pad = ops.head_pad(d)
@@ -103,5 +121,3 @@ def test_attention_row_max_jumps_between_tiles(cuda, dtype, variant, boost):
         assert bool(torch.isfinite(out.float()).all())
         err = ((out.float() - ref).norm() / ref.norm()).item()
         assert err < TOL[dtype], (variant, boost, err)
-    finally:
-        lib.tcl_debug_attention_variant(old)

@@ -5,7 +5,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
 from tclight_b200 import ops
-from tclight_b200._lib import lib
+from tclight_b200 import _lib
+lib = _lib.load_tuning_lib()
+assert lib is not None, "build the tuning library first: make -C tclight_b200/csrc tuning"
+ops.lib = lib            # ops.attention now calls the tuning build (include/tclight_tuning.h)
 
 
 def timeit(fn, iters=3, warm=1):

@@ -8,8 +8,12 @@ which = sys.argv[1] if len(sys.argv) > 1 else "attn"
 dev = torch.device("cuda"); dt = torch.bfloat16
 torch.manual_seed(0)
 if which.startswith("attn"):
-    from tclight_b200._lib import lib
-    lib.tcl_debug_attention_variant(int(which[4:] or 0))
+    var = int(which[4:] or -1)
+    if var != -1:                                    # tuning variants live in libtclight_tuning.so (include/tclight_tuning.h)
+        from tclight_b200 import _lib
+        lib = _lib.load_tuning_lib()
+        ops.lib = lib
+        lib.tcl_debug_attention_variant(var)
     B, H, T, d = 2, 8, 47520, 40
     dp = ops.head_pad(d); Tp = (T + 7) // 8 * 8
     q = torch.randn(B, H, Tp, dp, device=dev).to(dt); k = torch.randn(B, H, Tp, dp, device=dev).to(dt)

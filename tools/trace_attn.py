@@ -3,7 +3,9 @@ import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tclight_b200 import ops
-from tclight_b200._lib import lib
+from tclight_b200 import _lib
+lib = _lib.load_tuning_lib()      # needs a -DTCL_ATTN_TRACE tuning build: make -C tclight_b200/csrc tuning EXTRA=-DTCL_ATTN_TRACE
+ops.lib = lib
 
 var = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 dev = torch.device("cuda"); dt = torch.bfloat16
@@ -12,8 +14,6 @@ dp = ops.head_pad(d); Tp = (T + 7) // 8 * 8
 q = torch.randn(B, H, Tp, dp, device=dev).to(dt); k = torch.randn(B, H, Tp, dp, device=dev).to(dt)
 vt = torch.randn(B, H, dp, Tp, device=dev).to(dt)
 buf = torch.zeros(192, dtype=torch.int64, device=dev)
-lib.tcl_debug_attention_trace.argtypes = [C.c_void_p]
-lib.tcl_debug_attention_trace.restype = None
 lib.tcl_debug_attention_variant(var)
 ops.attention(q, k, vt, T, T, d)
 lib.tcl_debug_attention_trace(buf.data_ptr())
