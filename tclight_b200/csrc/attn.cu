@@ -623,7 +623,7 @@ xattn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ XAttn
     mbar_init(kv_full, 1);
     mbar_init(kv_empty, 1);
     for (int i = 0; i < XQST; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 512); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 512); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 16); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 16); }
     fence_barrier_init();
   }
   if (warp == 17) tmem_alloc<512>(tmem_slot);
@@ -737,8 +737,10 @@ xattn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ XAttn
           case 2: xsoft_part<BF16, POLY, K2>(t_s, K0 + K1, p.tk - K0 - K1, sc, xm, 2, row); break;
           default: xsoft_part<BF16, POLY, K3>(t_s, K0 + K1 + K2, p.tk - K0 - K1 - K2, sc, xm, 3, row); break;
         }
+        // one arrival per warp (512 per-thread arrivals on one shared-memory word serialise: ~2 000 clk per tile)
         tcgen05_fence_before();
-        mbar_arrive(&p_full[b]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[b]);
       }
       if (i > 0) {
         // ---- epilogue of tile i-1: O[:, :d] / O[:, d] ----
@@ -755,7 +757,8 @@ xattn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ XAttn
         if (quarter < ng) tmem_ld_32x32b_x16(t_o + 16 * quarter, v);
         tmem_ld_wait();
         tcgen05_fence_before();
-        mbar_arrive(&s_free[b]);              // this buffer's O is in registers: the P V of tile j+2 may overwrite it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[b]);   // this buffer's O is in registers: the P V of tile j+2 may overwrite it
         if (quarter < ng && tok < p.tq) {
           float l = 0.f;
 #pragma unroll

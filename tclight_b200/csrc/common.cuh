@@ -148,6 +148,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Pure spin on the non-blocking probe (no hardware sleep: the suspended try_wait wakes late, which matters where a short
+// per-tile chain crosses several barriers), with the same watchdog.
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if (++spins > (1u << 28)) {
+      printf("tclight: mbarrier watchdog (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // fences / proxies
 // ------------------------------------------------------------------------------------------
