@@ -665,6 +665,7 @@ level0_uvt_kernel(L0Params q, Shards sh, float inv_nseg) {
   const int* ids_cur = q.ids + (long long)fr * q.P;
   const int* ids_pre = q.ids + (long long)(fr > 0 ? fr - 1 : 0) * q.P;
   const float4* own1 = q.own1 + (long long)b * q.h1 * q.w1;
+  float* Gp = q.G_pre + (long long)b * 4 * q.P;     // sharded runs only: local image of the predecessor frame's gradient
   float acc_flow = 0.f, acc_tvh = 0.f, acc_tvw = 0.f;
 
   auto sink = [&](int id, unsigned fl, float g0, float g1, float g2) {
@@ -740,7 +741,7 @@ level0_uvt_kernel(L0Params q, Shards sh, float inv_nseg) {
         const float wy = bc.cy[j];
         const unsigned fl = (tf >> (3 * j)) & 7u;
         int id = 0;
-        if (main_on && fl) id = __ldg(ids_pre + o0 + j * q.W);
+        if (W1 && main_on && fl) id = __ldg(ids_pre + o0 + j * q.W);
         float v[4][3];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -753,7 +754,10 @@ level0_uvt_kernel(L0Params q, Shards sh, float inv_nseg) {
         for (int k = 1; k <= 3; ++k)
 #pragma unroll
           for (int c = 0; c < 3; ++c) out[c] = fmaf(__shfl_up_sync(FULL, v[k][c], k), accf[k], out[c]);
-        if (main_on && fl) sink(id, fl, out[0], out[1], out[2]);
+        if (main_on && fl) {
+          if (W1) sink(id, fl, out[0], out[1], out[2]);
+          else red_add_v4(Gp + (long long)(o0 + j * q.W) * 4, out[0], out[1], out[2]);     // sharded: see pre_sink_uvt_kernel
+        }
         if (left) {                                  // rare: broken chain / image border
           const int yy = bc.y0 + j;
           if (yy >= 0 && yy < q.H) {
@@ -762,7 +766,9 @@ level0_uvt_kernel(L0Params q, Shards sh, float inv_nseg) {
               const int xx = bc.x0 + i;
               if (!((left >> i) & 1u) || xx < 0 || xx >= q.W) continue;
               const unsigned fli = __float_as_uint(__ldg(Xp + yy * q.W + xx).w) & 7u;
-              if (fli) sink(ids_pre[yy * q.W + xx], fli, v[i][0], v[i][1], v[i][2]);
+              if (!fli) continue;
+              if (W1) sink(ids_pre[yy * q.W + xx], fli, v[i][0], v[i][1], v[i][2]);
+              else red_add_v4(Gp + (long long)(yy * q.W + xx) * 4, v[i][0], v[i][1], v[i][2]);
             }
           }
         }
@@ -816,6 +822,31 @@ level0_uvt_kernel(L0Params q, Shards sh, float inv_nseg) {
     float a = 0.f, bb = 0.f, cc = 0.f;
     for (int i = 0; i < 8; ++i) { a += red[0][i]; bb += red[1][i]; cc += red[2][i]; }
     atomicAdd(&q.scal[SC_FLOW_ABS], a); atomicAdd(&q.scal[SC_TV_H], bb); atomicAdd(&q.scal[SC_TV_W], cc);
+  }
+}
+
+// Sharded stage 2, predecessor half: under data parallelism most UVT rows live in a peer's memory and every reduction is
+// an NVLink transaction, so the (up to 4 per pixel) predecessor contributions are first summed in the LOCAL image G_pre
+// (local L2 reductions are nearly free) and leave as ONE 16-byte reduction per predecessor pixel: 2 instead of 5 remote
+// reductions per pixel.  Clears G_pre for the next iteration.
+__global__ void __launch_bounds__(256)
+pre_sink_uvt_kernel(L0Params q, Shards sh) {
+  const int b = blockIdx.y;
+  const int fr = q.bt.idx[b];
+  if (fr <= 0) return;
+  float4* Gp = reinterpret_cast<float4*>(q.G_pre + (long long)b * 4 * q.P);
+  const float4* Xpre = q.X + (long long)(q.bt.n + b) * q.P;
+  const int* ids_pre = q.ids + (long long)(fr - 1) * q.P;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < q.P; p += gridDim.x * blockDim.x) {
+    const float4 gv = Gp[p];
+    if (gv.x == 0.f && gv.y == 0.f && gv.z == 0.f) continue;
+    Gp[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned fl = __float_as_uint(Xpre[p].w) & 7u;
+    if (!fl) continue;
+    int owner, local;
+    shard_of<false>(sh, ids_pre[p], owner, local);
+    red_add_v4(sh.grad[owner] + (long long)local * 4, (fl & 1) ? gv.x * SH_C0 : 0.f, (fl & 2) ? gv.y * SH_C0 : 0.f,
+               (fl & 4) ? gv.z * SH_C0 : 0.f);
   }
 }
 
@@ -1296,7 +1327,11 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
     dim3 gu(gridp(chunks * 32, 256, 148 * 2), nb);
     const float inv_nseg = 1.f / (float)((W + SEG - 1) / SEG);
     if (w1) level0_uvt_kernel<true><<<gu, 256, 0, stream>>>(q, sh, inv_nseg);
-    else level0_uvt_kernel<false><<<gu, 256, 0, stream>>>(q, sh, inv_nseg);
+    else {
+      level0_uvt_kernel<false><<<gu, 256, 0, stream>>>(q, sh, inv_nseg);
+      TCL_CHECK_LAUNCH("postopt(level0)");
+      pre_sink_uvt_kernel<<<g0, 256, 0, stream>>>(q, sh);
+    }
     TCL_CHECK_LAUNCH("postopt(level0)");
   } else {
     level0_expo_kernel<<<g0, 256, 0, stream>>>(q);

@@ -248,17 +248,29 @@ def _dp_exposure_iteration(ctx, mine, n_global, n_valid_global, params, grad, m,
                             1e-8, step, stream_ptr()), "tcl_adam_step")
 
 
-def _dp_uvt_iteration(ctx, tab: UvtShardTable, mine, n_global, n_valid_global, m, v, ids, lr, step, loss_row):
-    """Stage 2: gather / scatter against the row shards over peer memory, barrier, Adam on the local shard, barrier."""
+def _dp_uvt_iteration(ctx, tab: UvtShardTable, mine, n_global, n_valid_global, m, v, ids, lr, step, loss_row, marks=None):
+    """Stage 2: gather / scatter against the row shards over peer memory, barrier, Adam on the local shard, barrier.
+    ``marks`` (measurement only): a list that receives five CUDA events bracketing the four phases."""
+    def mark():
+        if marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append(e)
+
     ctx.c.norm_batch, ctx.c.norm_valid = n_global, n_valid_global
+    mark()
     if mine:
         arr, nb = _idx_array(mine)
         check(lib.tcl_uvt_gradient_sharded(C.byref(ctx.c), arr, nb, ids.data_ptr(), C.byref(tab.c), loss_row.data_ptr(),
                                            stream_ptr()), "tcl_uvt_gradient_sharded")
+    mark()
     tab.barrier()
+    mark()
     check(lib.tcl_adam_step_uvt(tab.fdc_local.data_ptr(), tab.grad_local.data_ptr(), m.data_ptr(), v.data_ptr(), tab.rows, lr,
                                 0.9, 0.999, 1e-15, step, stream_ptr()), "tcl_adam_step_uvt")
+    mark()
     tab.barrier()
+    mark()
 
 
 def _idx_array(idxs) -> Tuple[C.Array, int]:
@@ -447,12 +459,14 @@ def bench_postopt(device, n_frames: int, H: int, W: int, iters: int = 20, rank: 
             row = losses[(step0 + i) % len(losses)]
             if world > 1:
                 mine, ng, nv = shard_batch(idxs, rank, world)
-                _dp_uvt_iteration(ctx, tab, mine, ng, nv, m, v, ids, lr, step0 + i + 1, row)
+                _dp_uvt_iteration(ctx, tab, mine, ng, nv, m, v, ids, lr, step0 + i + 1, row, marks=phase_marks)
                 continue
             arr, nb = _idx_array(idxs)
             check(lib.tcl_uvt_iteration(C.byref(ctx.c), arr, nb, ids.data_ptr(), U, fdc.data_ptr(), grad.data_ptr(), m.data_ptr(),
                                         v.data_ptr(), lr, 0.9, 0.999, 1e-15, step0 + i + 1, row.data_ptr(), stream_ptr()),
                   "tcl_uvt_iteration")
+
+    phase_marks = None
 
     def sync():
         if world > 1:
@@ -475,8 +489,27 @@ def bench_postopt(device, n_frames: int, H: int, W: int, iters: int = 20, rank: 
     e.record()
     sync()
     ms = max_over_ranks(s.elapsed_time(e) / iters)
+    phases = None
     if world > 1:
         import torch.distributed as dist
+        # a second, instrumented pass: events around the four phases of an iteration (this rank's view, mean over iterations)
+        phase_marks = []
+        run(min(iters, 10), 3 + iters)
+        sync()
+        k = len(phase_marks) // 5
+        acc = [0.0] * 4
+        for j in range(k):
+            ev = phase_marks[5 * j:5 * j + 5]
+            for q_ in range(4):
+                acc[q_] += ev[q_].elapsed_time(ev[q_ + 1])
+        mine_ms = torch.tensor([a / max(k, 1) for a in acc], device=device, dtype=torch.float64)
+        mx = mine_ms.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        mn = mine_ms.clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        names = ["gradient_kernels", "barrier_after_scatter", "adam_local_shard", "barrier_after_adam"]
+        phases = {n: {"min_ms": mn[i].item(), "max_ms": mx[i].item()} for i, n in enumerate(names)}
+        phase_marks = None
         dist.all_reduce(losses)
         tab.close()
     loss_fl = [losses[3, 0].item(), losses[(3 + iters - 1) % len(losses), 0].item()]
@@ -499,7 +532,7 @@ def bench_postopt(device, n_frames: int, H: int, W: int, iters: int = 20, rank: 
           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": kind, "unit": "GB/s", "frac": ach / peak,
                        "traffic": traffic.get("dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
                        "traffic_unit": "bytes/iteration (ncu dram__bytes_read+write summed over the iteration's kernels, 1 GPU)"},
-          "loss_first_last": loss_fl, "n_gpus": world,
+          "loss_first_last": loss_fl, "n_gpus": world, "phase_ms_over_ranks": phases,
           "parallelism": (f"batch-parallel x{world}; UVT rows + gradient sharded by row range, gathered / reduced through peer memory over "
                           "NVLink inside the gather and level-0 kernels, Adam on the local shard") if world > 1 else "single GPU",
           "note": "dense-Adam semantics (every UVT row updated every iteration, as torch.optim.Adam does)"}
