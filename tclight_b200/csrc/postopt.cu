@@ -675,12 +675,17 @@ level0_uvt_kernel(L0Params q, Shards sh, float inv_nseg) {
                (fl & 4) ? g2 * SH_C0 : 0.f);
   };
 
+  // A block's 8 warps take the same 29-pixel segment of 8 CONSECUTIVE image rows: their bicubic footprints (4 predecessor
+  // rows each) overlap by three quarters and the TV neighbours are each other's pixels, so the taps hit L1 instead of L2
+  // (the kernel was L2-bandwidth bound: 5 GB of L2 traffic per iteration with row-major chunking).
   const int n_seg = (q.W + SEG - 1) / SEG;
-  const int n_chunks = q.H * n_seg;
-  for (int ch = blockIdx.x * 8 + warp; ch < n_chunks; ch += gridDim.x * 8) {       // warp-uniform
-    int y = __float2int_rz(((float)ch + 0.5f) * inv_nseg);
-    if (y * n_seg > ch) --y; else if ((y + 1) * n_seg <= ch) ++y;
-    const int seg = ch - y * n_seg;
+  const int n_items = ((q.H + 7) >> 3) * n_seg;
+  for (int bi = blockIdx.x; bi < n_items; bi += gridDim.x) {                        // block-uniform
+    int grp = __float2int_rz(((float)bi + 0.5f) * inv_nseg);
+    if (grp * n_seg > bi) --grp; else if ((grp + 1) * n_seg <= bi) ++grp;
+    const int seg = bi - grp * n_seg;
+    const int y = grp * 8 + warp;
+    if (y >= q.H) continue;                                                          // warp-uniform
     const int x = seg * SEG - 3 + lane;
     const bool act = x >= 0 && x < q.W;
     const bool real = act && lane >= 3;
@@ -1323,8 +1328,8 @@ static int run_iteration(int stage, const tcl_postopt_ctx* c, const int* idx_hos
   q.edited = c->edited; q.G_pre = w.G_pre; q.scal = w.scal; q.ids = ids; q.grad_expo = egrad;
   dim3 g0(gridp(P, 256, 148 * 2), nb);
   if (stage == 2) {
-    const long long chunks = (long long)H * ((W + SEG - 1) / SEG);
-    dim3 gu(gridp(chunks * 32, 256, 148 * 2), nb);
+    const long long items = (long long)((H + 7) / 8) * ((W + SEG - 1) / SEG);      // one item = 8 rows x one segment = one block pass
+    dim3 gu(gridp(items * 256, 256, 148 * 2), nb);
     const float inv_nseg = 1.f / (float)((W + SEG - 1) / SEG);
     if (w1) level0_uvt_kernel<true><<<gu, 256, 0, stream>>>(q, sh, inv_nseg);
     else {
