@@ -111,8 +111,13 @@ typedef struct {
   const void* k;
   const void* vt;
   void* out;
+  void* workspace;        /* optional (may be NULL): >= tcl_attention_workspace_bytes() of device scratch.  With it, long
+                             self-attention launches cut the work items of their last, partial wave of CTAs into slices of
+                             the key range that run side by side, and merge the partial (O, max, denominator) results   */
+  size_t workspace_bytes;
 } tcl_attn_desc;
 
+size_t tcl_attention_workspace_bytes(void);
 int tcl_attention(const tcl_attn_desc* desc, tcl_stream_t stream);
 /* ---- normalisation / staging (HBM-bound) --------------------------------------------------
  * GroupNorm(+SiLU) of diffusers ResnetBlock2D / Transformer2DModel / conv_norm_out over NHWC,

@@ -132,11 +132,15 @@ class AttnDesc(C.Structure):
         ("k", C.c_void_p),
         ("vt", C.c_void_p),
         ("out", C.c_void_p),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_size_t),
     ]
 
 
 lib.tcl_attention.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
 lib.tcl_attention.restype = C.c_int
+lib.tcl_attention_workspace_bytes.argtypes = []
+lib.tcl_attention_workspace_bytes.restype = C.c_size_t
 
 TCL_LATENT_FP32 = 0
 TCL_LATENT_FP16 = 1

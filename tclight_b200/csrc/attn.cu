@@ -34,6 +34,12 @@ struct AttnParams {
   void* out;           // [B, tq, heads*d]
   long long out_pitch; // heads*d
   long long* trace;    // TCL_ATTN_TRACE builds only: clock64 event log of CTA (0,0)
+  // 1-D grid: CTA id -> (work item = cta_base + id / kv_parts, KV part = id % kv_parts); item -> (bh, Q tile group)
+  int q_groups;        // Q tile groups (NQ tiles each) per (batch, head)
+  int cta_base;        // first work item of this launch
+  int kv_parts;        // 1 = a CTA walks the whole key range and writes normalised output; > 1 = KV-split tail (below)
+  float* part_o;       // kv_parts > 1: un-normalised partial O [item - cta_base][part][NQ*128 rows][64] fp32 (column d = denominator)
+  float* part_m;       //               reference maximum (scaled, log2 domain) [item - cta_base][part][NQ*128 rows]
 };
 
 #ifdef TCL_ATTN_TRACE
@@ -132,7 +138,7 @@ __device__ __forceinline__ float2 poly_exp2_pair(float2 x) {
 template <int NQ, int REGS>
 constexpr int attn_threads() { return REGS > 0 ? 384 : NQ * 128 + 32 + NQ * 32; }
 
-template <int NQ, int DPAD, int KST, int VST, bool BF16, int POLY, bool PACKED, bool STALE, int MINB, int REGS>
+template <int NQ, int DPAD, int KST, int VST, bool BF16, int POLY, bool PACKED, bool STALE, int MINB, int REGS, bool SPLIT = false>
 __global__ void __launch_bounds__(attn_threads<NQ, REGS>(), MINB)
 attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnParams p) {
   using E = Elem<BF16>;
@@ -170,11 +176,18 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int bh = blockIdx.y;                       // q batch*heads index
+  // Normal launches: 2-D grid (Q tile group, batch*head) — measured 1.5-2.5 % faster than the same items on a 1-D grid; work
+  // items from p.cta_base on belong to the KV-split tail launch (SPLIT, 1-D grid: item = cta_base + id / kv_parts).
+  const int kv_parts = SPLIT ? p.kv_parts : 1;
+  const int part = SPLIT ? blockIdx.x % kv_parts : 0;
+  const int item = SPLIT ? p.cta_base + blockIdx.x / kv_parts : blockIdx.y * gridDim.x + blockIdx.x;
+  if (!SPLIT && item >= p.cta_base) return;        // (cta_base = all items when nothing is split off)
+  const int bh = SPLIT ? item / p.q_groups : blockIdx.y;
   const int b = bh / p.heads, head = bh - b * p.heads;
   const int kv_bh = (b / p.kv_batch_div) * p.heads + head;
-  const int q_row0 = blockIdx.x * (NQ * 128);
-  const int n_kv = p.n_kv_tiles;
+  const int q_row0 = (SPLIT ? item - bh * p.q_groups : blockIdx.x) * (NQ * 128);
+  const int kv0 = SPLIT ? (int)((long long)part * p.n_kv_tiles / kv_parts) : 0;          // this CTA's KV tiles [kv0, kv0 + n_kv)
+  const int n_kv = SPLIT ? (int)((long long)(part + 1) * p.n_kv_tiles / kv_parts) - kv0 : p.n_kv_tiles;
 
   if (threadIdx.x == SOFT_THREADS) {
     tma_prefetch_desc(&tm.q);
@@ -217,7 +230,7 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
           mbar_wait(&k_empty[st], ((kn / KST) & 1) ^ 1);
           mbar_arrive_expect_tx(&k_full[st], QK_TILE);
           for (int c = 0; c < NC; ++c)
-            tma_load_3d(smem + OFF_K + st * QK_TILE + c * 16384, &tm.k, &k_full[st], c * 64, j * 128, kv_bh);
+            tma_load_3d(smem + OFF_K + st * QK_TILE + c * 16384, &tm.k, &k_full[st], c * 64, (kv0 + j) * 128, kv_bh);
           ++kn;
         }
         {
@@ -225,7 +238,7 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
           mbar_wait(&v_empty[st], ((vn / VST) & 1) ^ 1);
           mbar_arrive_expect_tx(&v_full[st], v_bytes);
           for (int c = 0; c < 2; ++c)
-            tma_load_3d(smem + OFF_V + st * V_TILE + c * V_CHUNK, &tm.vt, &v_full[st], j * 128 + c * 64, 0, kv_bh);
+            tma_load_3d(smem + OFF_V + st * V_TILE + c * V_CHUNK, &tm.vt, &v_full[st], (kv0 + j) * 128 + c * 64, 0, kv_bh);
           ++vn;
         }
       }
@@ -372,7 +385,7 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
       tmem_ld_32x32b_x32(t_s + 96, s3);
       const bool pe_ready = mbar_test_wait(&p_empty[q], (j & 1) ^ 1);   // P V of the previous tile: consumed after the exps
       tmem_ld_wait();
-      const int valid_cols = p.tk - j * 128;
+      const int valid_cols = p.tk - (kv0 + j) * 128;
       const bool tail = valid_cols < 128;      // warp-uniform: only the last KV tile
       if (tail) { mask_chunk(s0, 0, valid_cols); mask_chunk(s1, 32, valid_cols); mask_chunk(s2, 64, valid_cols); mask_chunk(s3, 96, valid_cols); }
       uint32_t pk[64];
@@ -464,6 +477,23 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
     mbar_wait(&o_full[q], 0);
     tcgen05_fence_after();
     const int t = q_row0 + q * 128 + row;
+    if (SPLIT) {
+      // KV-split tail: this CTA saw only a slice of the keys.  O is consistent with m_ref here (the lazy rescale is applied
+      // before every P V; the stale-reference variants, which owe a factor, are never split), so (O, m_ref) can be merged.
+      const long long prow = ((long long)(blockIdx.x / kv_parts) * kv_parts + part) * (NQ * 128) + q * 128 + row;
+      float* po = p.part_o + prow * 64;
+      p.part_m[prow] = m_ref;
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.n_o; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_o + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(po + c0 + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                                                __uint_as_float(v[i + 3]));
+      }
+    } else {
     float inv_l;
     {
       uint32_t v[16];
@@ -490,6 +520,7 @@ attn_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnPa
         *reinterpret_cast<uint4*>(out + c0) = make_uint4(o[0], o[1], o[2], o[3]);
         if (c0 + 8 < p.d) *reinterpret_cast<uint4*>(out + c0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
       }
+    }
     }
   }
 
@@ -800,8 +831,43 @@ static int launch_xattn(const AttnTmaps& tm, const XAttnParams& p, int grid, cud
   return TCL_OK;
 }
 
+// Merge of the KV-split tail: out[row] = sum_s 2^(m_s - m) O_s / sum_s 2^(m_s - m) l_s  (l_s = column d of O_s).
+// grid (rows / 32, tail items), block (8 column groups, 32 rows): thread (cg, r) handles columns cg*8 .. cg*8+7 of one row.
+template <bool BF16>
+__global__ void attn_merge_kernel(AttnParams p, int rows_per_item) {
+  using E = Elem<BF16>;
+  const int it = blockIdx.y;
+  const int row = blockIdx.x * 32 + threadIdx.y;
+  const int item = p.cta_base + it;
+  const int bh = item / p.q_groups;
+  const int b = bh / p.heads, head = bh - b * p.heads;
+  const int t = (item - bh * p.q_groups) * rows_per_item + row;
+  if (t >= p.tq) return;
+  const int c0 = threadIdx.x * 8;
+  if (c0 >= p.d) return;
+  const long long base = (long long)it * p.kv_parts * rows_per_item + row;
+  float m = -INFINITY;
+  for (int s = 0; s < p.kv_parts; ++s) m = fmaxf(m, p.part_m[base + (long long)s * rows_per_item]);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float l = 0.f;
+  for (int s = 0; s < p.kv_parts; ++s) {
+    const long long pr = base + (long long)s * rows_per_item;
+    const float w = fast_exp2(p.part_m[pr] - m);
+    const float* po = p.part_o + pr * 64;
+    l += w * po[p.d];
+    const float4 a = *reinterpret_cast<const float4*>(po + c0), bq = *reinterpret_cast<const float4*>(po + c0 + 4);
+    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+    acc[4] += w * bq.x; acc[5] += w * bq.y; acc[6] += w * bq.z; acc[7] += w * bq.w;
+  }
+  const float inv_l = 1.0f / l;
+  typename E::T* out = reinterpret_cast<typename E::T*>(p.out) + (static_cast<long long>(b) * p.tq + t) * p.out_pitch + head * p.d + c0;
+  *reinterpret_cast<uint4*>(out) = make_uint4(E::pack(acc[0] * inv_l, acc[1] * inv_l), E::pack(acc[2] * inv_l, acc[3] * inv_l),
+                                              E::pack(acc[4] * inv_l, acc[5] * inv_l), E::pack(acc[6] * inv_l, acc[7] * inv_l));
+}
+
 template <int NQ, int DPAD, int KST, int VST, bool BF16, int POLY, bool PACKED, bool STALE, int MINB = 1, int REGS = 0>
-static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, int bh, cudaStream_t stream) {
+static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, int bh, cudaStream_t stream,
+                       void* split_ws = nullptr, size_t split_ws_bytes = 0) {
   constexpr size_t smem = (size_t)NQ * 128 * DPAD * 2 + (size_t)KST * 128 * DPAD * 2 + (size_t)VST * 2 * DPAD * 128 + 1024 + 256;
   static bool configured = false;
   if (!configured) {
@@ -813,10 +879,54 @@ static int launch_attn(const AttnTmaps& tm, const AttnParams& p, int q_tiles, in
     }
     configured = true;
   }
-  dim3 grid((q_tiles + NQ - 1) / NQ, bh);
   static_assert(REGS == 0 || (NQ == 2 && REGS % 8 == 0 && (4 * 88 + 8 * REGS) * 32 <= 65536), "register split");
-  attn_kernel<NQ, DPAD, KST, VST, BF16, POLY, PACKED, STALE, MINB, REGS><<<grid, attn_threads<NQ, REGS>(), smem, stream>>>(tm, p);
+  AttnParams q = p;
+  q.q_groups = (q_tiles + NQ - 1) / NQ;
+  const int items = q.q_groups * bh;
+  q.cta_base = 0; q.kv_parts = 1;
+  int main_items = items;
+  // KV-split tail (no stale reference: see the epilogue).  The last, partial wave of CTAs would keep most SMs idle for a whole
+  // tile time (T = 47 520, d = 40: 2 976 CTAs = 20.1 waves of 148); its work items are cut into kv_parts slices of the key
+  // range that run side by side, and a small kernel merges the (O, max, denominator) partials.
+  int parts = 1, tail = 0;
+  if (!STALE && split_ws && NQ == 2) {
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    tail = items % sms;
+    // only when the tail leaves at least three quarters of the SMs idle: with 2-3 slices the extra launches and the merge
+    // cost more than the shorter last wave saves (measured at T = 11 520: 0.605 -> 0.620 ms with 2 slices)
+    if (items > sms && tail > 0 && tail * 4 <= sms) {
+      parts = sms / tail;
+      if (parts > 16) parts = 16;
+      while (parts > 1 && p.n_kv_tiles / parts < 8) --parts;          // a slice keeps at least 8 KV tiles
+      const size_t need = (size_t)tail * parts * NQ * 128 * (64 + 1) * sizeof(float);
+      if (parts > 1 && need <= split_ws_bytes) main_items = items - tail; else parts = 1;
+    }
+  }
+  q.cta_base = main_items;                     // the normal launch skips the items the tail launch takes
+  attn_kernel<NQ, DPAD, KST, VST, BF16, POLY, PACKED, STALE, MINB, REGS><<<dim3(q.q_groups, bh), attn_threads<NQ, REGS>(), smem, stream>>>(tm, q);
   TCL_CHECK_LAUNCH("tcl_attention");
+  if (parts > 1) {
+    q.kv_parts = parts;
+    q.part_o = reinterpret_cast<float*>(split_ws);
+    q.part_m = q.part_o + (size_t)tail * parts * NQ * 128 * 64;
+    if constexpr (!STALE && NQ == 2) {
+      static bool configured_split = false;
+      if (!configured_split) {
+        cudaError_t e = cudaFuncSetAttribute(attn_kernel<NQ, DPAD, KST, VST, BF16, POLY, PACKED, STALE, MINB, REGS, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+          set_last_error("attention: cudaFuncSetAttribute(%zu B) failed: %s", smem, cudaGetErrorString(e));
+          return TCL_ERR_CUDA;
+        }
+        configured_split = true;
+      }
+      attn_kernel<NQ, DPAD, KST, VST, BF16, POLY, PACKED, STALE, MINB, REGS, true><<<tail * parts, attn_threads<NQ, REGS>(), smem, stream>>>(tm, q);
+    }
+    TCL_CHECK_LAUNCH("tcl_attention(tail)");
+    attn_merge_kernel<BF16><<<dim3(NQ * 128 / 32, tail), dim3(8, 32), 0, stream>>>(q, NQ * 128);
+    TCL_CHECK_LAUNCH("tcl_attention(merge)");
+  }
   return TCL_OK;
 }
 
@@ -836,6 +946,13 @@ constexpr int g_attn_variant = -1;
 constexpr int g_attn_trim = 1;
 constexpr long long* g_attn_trace = nullptr;
 #endif
+
+extern "C" size_t tcl_attention_workspace_bytes(void) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; }
+  return (size_t)sms * 256 * (64 + 1) * sizeof(float);        // <= one wave of KV-split CTAs x 256 rows x (O row + max)
+}
 
 extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
   TCL_CHECK_ARG(a != nullptr, "tcl_attention: null descriptor");
@@ -860,6 +977,7 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
   p.out = a->out;
   p.out_pitch = (long long)a->heads * a->d;
   p.trace = g_attn_trace;
+  p.q_groups = 0; p.cta_base = 0; p.kv_parts = 1; p.part_o = nullptr; p.part_m = nullptr;      // set per launch
   AttnTmaps tm;
   {
     const uint64_t dims[3] = {(uint64_t)a->d_pad, (uint64_t)a->tq, (uint64_t)bh};
@@ -937,8 +1055,8 @@ extern "C" int tcl_attention(const tcl_attn_desc* a, cudaStream_t stream) {
       }
     }
 #endif
-    return bf16 ? launch_attn<2, 64, 4, 3, true, 0x11, true, false, 1, 200>(tm, p, q_tiles, bh, stream)
-                : launch_attn<2, 64, 4, 3, false, 0x11, true, false, 1, 200>(tm, p, q_tiles, bh, stream);
+    return bf16 ? launch_attn<2, 64, 4, 3, true, 0x11, true, false, 1, 200>(tm, p, q_tiles, bh, stream, a->workspace, a->workspace_bytes)
+                : launch_attn<2, 64, 4, 3, false, 0x11, true, false, 1, 200>(tm, p, q_tiles, bh, stream, a->workspace, a->workspace_bytes);
   } else if (a->d_pad == 128) {
     // one Q tile per CTA (TMEM: 128 S + 128 O + 64 P): registers are plentiful, the stale-reference softmax wins (+8 %)
 #ifdef TCL_ATTN_TUNING

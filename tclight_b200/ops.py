@@ -201,12 +201,17 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, tq: int, tk: i
     a.kv_batch_div = kv_batch_div
     a.tq_pitch, a.tk_pitch = tq_pitch, tk_pitch
     a.q, a.k, a.vt, a.out = q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr()
+    ws = _attn_ws.get(q.device)
+    if ws is None:
+        ws = _attn_ws[q.device] = torch.empty(L.lib.tcl_attention_workspace_bytes(), device=q.device, dtype=torch.uint8)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     with _Prof(f"attention_d{d_pad}", 4.0 * B * H * tq * tk * d):
         check(lib.tcl_attention(C.byref(a), stream_ptr()), "tcl_attention")
     return out
 
 
 _gn_ws = {}
+_attn_ws = {}        # per device: scratch of the KV-split attention tail (tcl_attention_workspace_bytes)
 
 
 def _stats_ws(dev, n):

@@ -121,3 +121,27 @@ def test_attention_row_max_jumps_between_tiles(cuda, dtype, variant, boost):
         assert bool(torch.isfinite(out.float()).all())
         err = ((out.float() - ref).norm() / ref.norm()).item()
         assert err < TOL[dtype], (variant, boost, err)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("T", [4800, 4700, 5000])
+def test_attention_kv_split_tail(cuda, dtype, T):
+    """Launches whose CTA count leaves a small partial last wave (here 8 heads x 19-20 Q tile groups = 152-160 work items on
+    148 SMs) run that tail as KV-split CTAs + a merge kernel: the result must meet the same tolerance, including a ragged last
+    key tile (T = 4700, 5000) and rows beyond tq in the last Q tile."""
+    from tclight_b200 import ops
+
+    B, H, d = 1, 8, 40
+    torch.manual_seed(1)
+    d_pad = ops.head_pad(d)
+    q, qp = _mk(B, H, T, d, d_pad, dtype, cuda, 1.5)
+    k, kp = _mk(B, H, T, d, d_pad, dtype, cuda, 1.5)
+    v, vp = _mk(B, H, T, d, d_pad, dtype, cuda)
+    out = ops.attention(qp, kp, vp.transpose(2, 3).contiguous(), T, T, d)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float()).permute(0, 2, 1, 3).reshape(B, T, H * d)
+    assert bool(torch.isfinite(out.float()).all())
+    err = ((out.float() - ref).norm() / ref.norm()).item()
+    # the rows of the tail items specifically (the last work items in launch order = the last Q tile groups of the last head)
+    tail_rows = slice(T - 256, T)
+    err_tail = ((out.float()[:, tail_rows, -d:] - ref[:, tail_rows, -d:]).norm() / ref[:, tail_rows, -d:].norm()).item()
+    assert err < TOL[dtype] and err_tail < TOL[dtype], (T, err, err_tail)
