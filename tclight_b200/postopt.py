@@ -356,22 +356,25 @@ def unique_tensor_optimization(gen) -> Tuple[torch.Tensor, List[float]]:
     losses = torch.zeros((n_it, 3), device=dev, dtype=torch.float32)
     step = 0
     loader = batch_iterator(N, Bo)
-    for epoch in range(gen.epochs):
-        for idxs in loader:
-            step += 1
-            if world > 1:
-                mine, ng, nv = shard_batch(idxs, rank, world)
-                _dp_uvt_iteration(ctx, tab, mine, ng, nv, m, v, ids, feature_lr, step, losses[step - 1])
-                continue
-            arr, nb = _idx_array(idxs)
-            check(lib.tcl_uvt_iteration(C.byref(ctx.c), arr, nb, ids.data_ptr(), U, fdc.data_ptr(), grad.data_ptr(), m.data_ptr(),
-                                        v.data_ptr(), feature_lr, 0.9, 0.999, 1e-15, step, losses[step - 1].data_ptr(), stream_ptr()),
-                  "tcl_uvt_iteration")
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(losses)
-        fdc = tab.gather_full()
-        tab.close()
+    try:
+        for epoch in range(gen.epochs):
+            for idxs in loader:
+                step += 1
+                if world > 1:
+                    mine, ng, nv = shard_batch(idxs, rank, world)
+                    _dp_uvt_iteration(ctx, tab, mine, ng, nv, m, v, ids, feature_lr, step, losses[step - 1])
+                    continue
+                arr, nb = _idx_array(idxs)
+                check(lib.tcl_uvt_iteration(C.byref(ctx.c), arr, nb, ids.data_ptr(), U, fdc.data_ptr(), grad.data_ptr(), m.data_ptr(),
+                                            v.data_ptr(), feature_lr, 0.9, 0.999, 1e-15, step, losses[step - 1].data_ptr(), stream_ptr()),
+                      "tcl_uvt_iteration")
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(losses)
+            fdc = tab.gather_full()
+    finally:
+        if tab is not None:
+            tab.close()          # unmaps the peers' shards and frees this rank's (collective: every rank reaches it)
     images = torch.empty((N, 3, H, W), device=dev, dtype=torch.float32)
     check(lib.tcl_uvt_render(fdc.data_ptr(), ids.data_ptr(), N, H, W, images.data_ptr(), stream_ptr()), "tcl_uvt_render")
     gen._features_dc = fdc
